@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""Generate the committed golden traces from the LIVE Python reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+Every trace is produced by stepping the *unmodified* reference
+(`multiagent.environment.MultiAgentGraphEnv` + the july scenario, or the classic
+`onpolicy.envs.mpe` force step) through the import shims in
+`oracle/ref_harness.py`.  A trace holds the initial condition, the action stream,
+the random draws the step consumed (teacher-forcing inputs) and every
+per-step output of the path.  The reference publishes no golden vectors of its own
+(SURVEY.md section 4), so these files ARE the golden set; regenerate only when the
+reference changes.
+"""
+from __future__ import annotations
+
+import ast
+import json
+import os
+import sys
+import textwrap
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_harness import (  # noqa: E402
+    REFERENCE_ROOT,
+    build_july_env,
+    install_shims,
+    july_args,
+)
+
+INFO_KEYS = [
+    "Dist_to_goal", "Time_req_to_goal", "Num_agent_collisions", "Num_obst_collisions",
+    "Distance_mean", "Distance_variance", "Mean_by_variance", "Dists_traveled",
+    "Time_taken", "Time_mean", "Time_stddev", "Time_mean_by_stddev", "Conformance",
+    "Delta_spacing", "Spacing_violations", "Min_time_to_goal",
+]
+
+
+def load_process_adj():
+    """Execute the reference's own `process_adj` source text (gnn_new.py:328-358)
+    without importing its module (torch_geometric is absent here)."""
+    import torch
+    from torch import Tensor
+    from typing import Tuple
+
+    path = os.path.join(REFERENCE_ROOT, "onpolicy/algorithms/utils/gnn_new.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "process_adj":
+            node.decorator_list = []
+            code = ast.unparse(node)
+            ns = {"torch": torch, "Tensor": Tensor, "Tuple": Tuple}
+            exec(textwrap.dedent(code), ns)
+            return ns["process_adj"]
+    raise RuntimeError("process_adj not found")
+
+
+def wrap_pi(a):
+    return (a + np.pi) % (2 * np.pi) - np.pi
+
+
+class PursuitPolicy:
+    """Goal-seeking action stream so that all three phases, the gate bonus and
+    goal-reach events occur inside a 200-step episode (random actions alone never
+    leave phase 0).  `eps` mixes in uniform random actions."""
+
+    def __init__(self, env, scenario, rs, eps):
+        self.env, self.sc, self.rs, self.eps = env, scenario, rs, eps
+        self.stage = [0] * env.n
+
+    def reset(self):
+        self.stage = [0] * self.env.n
+
+    def act(self):
+        w = self.env.world
+        tp = w.tube_params
+        e = np.asarray(tp["e"], dtype=np.float64)
+        out = []
+        for i, ag in enumerate(w.agents):
+            p = ag.state.p_pos
+            if self.rs.rand() < self.eps:
+                out.append(int(self.rs.randint(25)))
+                continue
+            if self.stage[i] == 0:
+                tgt = tp["entrance"] - 0.3 * e
+                if np.linalg.norm(tgt - p) < 0.12:
+                    self.stage[i] = 1
+            if self.stage[i] == 1:
+                tgt = tp["exit"] + 0.3 * e
+                if np.dot(p - tp["exit"], e) > 0.12:
+                    self.stage[i] = 2
+            if self.stage[i] == 2:
+                tgt = self.sc.landmark_poses[i]
+            err = wrap_pi(np.arctan2(tgt[1] - p[1], tgt[0] - p[0]) - ag.state.theta)
+            omegas = np.linspace(-0.5, 0.5, 5)
+            ar = int(np.argmin(np.abs(omegas - np.clip(err, -0.5, 0.5))))
+            ac = 4 if abs(err) < 0.6 else 0
+            out.append(ar * 5 + ac)
+        return np.array(out, dtype=np.int64)
+
+
+def tube_vector(w):
+    tp = w.tube_params
+    return np.array(
+        [tp["entrance"][0], tp["entrance"][1], tp["exit"][0], tp["exit"][1],
+         tp["e"][0], tp["e"][1], float(tp["n"][0]), float(tp["n"][1]),
+         tp["L"], tp["half_width"], tp["width"], tp["angle"]], dtype=np.float64)
+
+
+def snapshot_init(env, sc):
+    w = env.world
+    return dict(
+        agent_state=np.array([a.state.values.copy() for a in w.agents]),
+        prev_phase=np.array([getattr(a, "previous_phase", 0) for a in w.agents], dtype=np.int64),
+        tube=tube_vector(w),
+        landmarks=np.array([l.state.p_pos.copy() for l in w.landmarks]),
+        obstacles=np.array([o.state.p_pos.copy() for o in w.obstacles]).reshape(-1, 2),
+        goal_min_time=np.array([a.goal_min_time for a in w.agents]),
+    )
+
+
+def counters(env, sc):
+    w = env.world
+    n = env.n
+    c = np.zeros((n, 8), dtype=np.int64)
+    c[:, 0] = sc.spacing_violation
+    c[:, 1] = sc.steps_in_corridor
+    c[:, 2] = sc.conformance_percent
+    c[:, 3] = w.num_agent_collisions
+    c[:, 4] = w.num_obstacle_collisions
+    c[:, 5] = w.times_required
+    c[:, 6] = w.dists_to_goal
+    c[:, 7] = w.dist_left_to_goal
+    return c
+
+
+def pad_edges(edge_list, weight, cap):
+    ei = -np.ones((2, cap), dtype=np.int64)
+    ea = np.zeros(cap)
+    k = edge_list.shape[1]
+    ei[:, :k] = edge_list
+    ea[:k] = weight
+    return ei, ea, k
+
+
+def run_july_trace(path, seed, T, policy, eps=0.15, episodes=1, **over):
+    """One env, `episodes` episodes of T steps each (re-reset by the harness with the
+    reference's own reset()), outputs concatenated; `ep_start` marks reset rows."""
+    import torch
+
+    process_adj = load_process_adj()
+    args = july_args(episode_length=T, **over)
+    env, sc = build_july_env(args, seed)
+    env.seed(seed)
+    rs = np.random.RandomState(seed + 12345)
+    n = env.n
+    E = len(env.world.entities)
+    cap = E * (E - 1)
+    pol = PursuitPolicy(env, sc, rs, eps)
+
+    rec = {k: [] for k in (
+        "actions theta_draw state p_dist status prev_phase phase_reached goal_reached obs node_obs adj "
+        "reward done info cnt delta_spacing_sum edge_index edge_attr num_edges "
+        "gnn_edge_index gnn_edge_attr gnn_num_edges").split()}
+    inits = {k: [] for k in "agent_state prev_phase tube landmarks obstacles goal_min_time reset_obs reset_node_obs reset_adj".split()}
+
+    for ep in range(episodes):
+        obs_n, id_n, node_n, adj_n = env.reset(ep)
+        pol.reset()
+        ini = snapshot_init(env, sc)
+        for k, v in ini.items():
+            inits[k].append(v)
+        inits["reset_obs"].append(np.array(obs_n))
+        inits["reset_node_obs"].append(np.array(node_n))
+        inits["reset_adj"].append(np.array(adj_n[0]).copy())
+        for t in range(T):
+            a = pol.act() if policy == "pursuit" else rs.randint(25, size=n)
+            status_before = np.array([bool(ag.status) for ag in env.world.agents])
+            obs_n, id_n, node_n, adj_n, rew_n, done_n, info_n = env.step([np.eye(25)[i] for i in a])
+            w = env.world
+            status_after = np.array([bool(ag.status) for ag in w.agents])
+            th = np.full(n, np.nan)
+            for i in range(n):
+                if status_after[i] and not status_before[i]:
+                    th[i] = w.agents[i].state.theta  # the reset_velocity() draw (core.py:328)
+            assert all(x is adj_n[0] for x in adj_n)
+            adj = np.array(adj_n[0]).copy()
+            # env-side edges on the CURRENT masked matrix (what the next step's
+            # update_graph call would produce, environment.py:1022-1023)
+            sc.update_graph(w)
+            ei, ea, ne = pad_edges(w.edge_list, w.edge_weight, cap)
+            # consumer-side edges: reference process_adj on the fp32 cast the buffer makes
+            gi, ga = process_adj(torch.from_numpy(adj.astype(np.float32)), float(args.max_edge_dist))
+            gei, gea, gne = pad_edges(gi.numpy(), ga.numpy()[:, 0].astype(np.float64), cap)
+            rec["actions"].append(a)
+            rec["theta_draw"].append(th)
+            rec["state"].append(np.array([ag.state.values.copy() for ag in w.agents]))
+            rec["p_dist"].append(np.array([ag.state.p_dist for ag in w.agents]))
+            rec["status"].append(status_after)
+            rec["prev_phase"].append(np.array([ag.previous_phase for ag in w.agents]))
+            rec["phase_reached"].append(sc.phase_reached.copy())
+            rec["goal_reached"].append(sc.goal_reached.copy())
+            rec["obs"].append(np.array(obs_n))
+            rec["node_obs"].append(np.array(node_n))
+            rec["adj"].append(adj)
+            rec["reward"].append(np.array(rew_n, dtype=np.float64).reshape(n))
+            rec["done"].append(np.array(done_n, dtype=bool))
+            rec["info"].append(np.array([[float(info_n[i][k]) for k in INFO_KEYS] for i in range(n)]))
+            rec["cnt"].append(counters(env, sc))
+            rec["delta_spacing_sum"].append(float(np.sum(sc.delta_spacing)))
+            rec["edge_index"].append(ei); rec["edge_attr"].append(ea); rec["num_edges"].append(ne)
+            rec["gnn_edge_index"].append(gei); rec["gnn_edge_attr"].append(gea); rec["gnn_num_edges"].append(gne)
+
+    out = {k: np.array(v) for k, v in rec.items()}
+    out.update({"init_" + k if not k.startswith("reset_") else k: np.array(v) for k, v in inits.items()})
+    out["cfg_json"] = np.array(json.dumps({k: v for k, v in vars(args).items()}))
+    out["episodes"] = np.array(episodes)
+    out["T"] = np.array(T)
+    out["individual_reward_check"] = np.array(1)
+    np.savez_compressed(path, **out)
+    st = out["status"]
+    print(f"{os.path.basename(path)}: N={n} E={E} T={T}x{episodes} reached={int(st[-1].sum())} "
+          f"phases={sorted(set(out['obs'][..., 18].ravel().tolist()))} "
+          f"rew[{out['reward'].min():.2f},{out['reward'].max():.2f}] size={os.path.getsize(path)//1024}KB")
+
+
+def main():
+    install_shims()
+    g = lambda name: os.path.join(HERE, name)
+    # C3: july / air_taxi / N=3 -- README.md:84-105 flags
+    run_july_trace(g("july_n3_pursuit_s1.npz"), seed=1, T=200, policy="pursuit")
+    run_july_trace(g("july_n3_pursuit_s2.npz"), seed=2, T=200, policy="pursuit", eps=0.3)
+    run_july_trace(g("july_n3_pursuit_s3_ep3.npz"), seed=3, T=120, policy="pursuit", episodes=3)
+    run_july_trace(g("july_n3_random_s4.npz"), seed=4, T=200, policy="random")
+    run_july_trace(g("july_n3_collab_s5.npz"), seed=5, T=100, policy="pursuit", collaborative=True)
+    # wider worlds (C5 family): N=8 and N=16
+    run_july_trace(g("july_n8_pursuit_s6.npz"), seed=6, T=150, policy="pursuit",
+                   num_agents=8, num_landmarks=8, world_size=5)
+    run_july_trace(g("july_n16_pursuit_s7.npz"), seed=7, T=60, policy="pursuit",
+                   num_agents=16, num_landmarks=16, world_size=8)
+    # C5: N=64, world_size=12 (node_obs is 512 KB/step in fp64 -> keep T tiny)
+    run_july_trace(g("july_n64_pursuit_s8.npz"), seed=8, T=4, policy="pursuit",
+                   num_agents=64, num_landmarks=64, world_size=12)
+    # unicycle dynamics through the same scenario (P3 patch)
+    from multiagent.config import UnicycleVehicleConfig
+    UnicycleVehicleConfig.COORDINATION_RANGE = UnicycleVehicleConfig.COMMUNICATION_RANGE
+    run_july_trace(g("july_n3_unicycle_s9.npz"), seed=9, T=120, policy="pursuit", dynamics_type="unicycle_vehicle")
+
+
+if __name__ == "__main__":
+    main()
