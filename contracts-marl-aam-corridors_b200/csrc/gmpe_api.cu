@@ -1,0 +1,235 @@
+// gmpe_api.cu -- C ABI (include/gmpe.h) over the fused step kernel.
+// Built by csrc/build.py:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -shared
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "gmpe_step.cuh"
+
+using namespace gmpe;
+
+struct gmpe_ctx {
+  GmpeConfig cfg;
+  int device;
+  int sm_count;
+  int threads;
+  int wpb;
+  int num_tiles;
+  int grid;
+  size_t smem_bytes;
+  int64_t launches;
+  std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(gmpe_ctx* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+
+static const char* validate(const GmpeConfig& c) {
+  if (c.scenario != GMPE_SCEN_JULY_TUBE && c.scenario != GMPE_SCEN_NAV_GRAPH) return "unknown scenario";
+  if (c.dynamics < 0 || c.dynamics > 2) return "unknown dynamics";
+  if (c.physics != GMPE_PHYS_KINEMATIC && c.physics != GMPE_PHYS_FORCE) return "unknown physics";
+  if (c.precision != GMPE_F32 && c.precision != GMPE_F64) return "unknown precision";
+  if (c.num_worlds < 1) return "num_worlds must be >= 1";
+  if (c.num_agents < 1 || c.num_agents > GMPE_MAX_AGENTS) return "num_agents out of range [1, 64]";
+  if (c.num_landmarks < c.num_agents) return "num_landmarks must be >= num_agents";
+  if (c.num_obstacles < 0 || c.num_walls < 0) return "negative entity count";
+  if (c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls > GMPE_MAX_ENTITIES) return "too many entities";
+  if (c.scenario == GMPE_SCEN_JULY_TUBE && (c.num_obstacles || c.num_walls))
+    return "july tube scenario supports num_obstacles == num_walls == 0 only (the reference graph builder raises, SURVEY G7)";
+  if (c.physics == GMPE_PHYS_FORCE && c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR) return "force physics needs double_integrator state";
+  if (c.dynamics == GMPE_DYN_DOUBLE_INTEGRATOR && c.total_actions != 5 && c.total_actions != 9) return "double_integrator: total_actions must be 5 or 9";
+  if (c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR && c.total_actions != 25) return "unicycle / air_taxi use the 25 motion primitives";
+  if (c.episode_length < 1) return "episode_length must be >= 1";
+  if (!(c.world_size > 0)) return "world_size must be positive";
+  return nullptr;
+}
+
+static void plan_tiles(const GmpeConfig& c, int threads, int* wpb, int* tiles) {
+  int w = (threads / c.num_agents) & ~3;  // multiple of 4: every tile's output slab starts 16-byte aligned
+  if (w < 4) w = 4;
+  *wpb = w;
+  *tiles = (c.num_worlds + w - 1) / w;
+}
+
+template <typename Real>
+static size_t smem_for(const GmpeConfig& c, int wpb) {
+  int E = c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls;
+  int F = c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
+  return smem_layout<Real>(wpb, c.num_agents, E, c.num_walls, F, nullptr, nullptr);
+}
+
+extern "C" {
+
+int gmpe_abi_version(void) { return GMPE_ABI_VERSION; }
+
+int gmpe_layout(const GmpeConfig* cfg, GmpeLayout* out) {
+  if (!cfg || !out) return GMPE_E_NULL;
+  if (validate(*cfg)) return GMPE_E_INVALID;
+  const int64_t B = cfg->num_worlds, N = cfg->num_agents, L = cfg->num_landmarks, O = cfg->num_obstacles, W = cfg->num_walls;
+  const int64_t E = N + L + O + W;
+  out->real_bytes = cfg->precision == GMPE_F64 ? 8 : 4;
+  out->num_entities = (int32_t)E;
+  out->obs_dim = cfg->scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
+  out->node_dim = 8;
+  out->edge_cap = (int32_t)(E * (E - 1));
+  out->info_dim = GMPE_INFO_K;
+  out->agent_state = B * N * 4;
+  out->agent_aux = B * N * 2;
+  out->agent_flags = B * N * 4;
+  out->agent_cnt = B * N * GMPE_AGENT_CNT;
+  out->world_f = B * GMPE_WORLD_F;
+  out->world_i = B * GMPE_WORLD_I;
+  out->landmarks = B * L * 2;
+  out->obstacles = B * O * 2;
+  out->walls = B * W * GMPE_WALL_F;
+  out->obs = B * N * out->obs_dim;
+  out->node_obs = B * N * E * 8;
+  out->adj = B * E * E;
+  out->reward = B * N;
+  out->done = B * N;
+  out->info = B * N * GMPE_INFO_K;
+  out->edge_index = B * 2 * out->edge_cap;
+  out->edge_attr = B * out->edge_cap;
+  out->num_edges = B;
+  return GMPE_OK;
+}
+
+int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
+  if (!cfg || !out) return fail(nullptr, GMPE_E_NULL, "gmpe_create: NULL argument");
+  if (const char* why = validate(*cfg)) return fail(nullptr, GMPE_E_INVALID, std::string("gmpe_create: ") + why);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev)
+    return fail(nullptr, GMPE_E_CUDA, std::string("gmpe_create: no such CUDA device (") + cudaGetErrorString(e) + ")");
+  gmpe_ctx* h = new (std::nothrow) gmpe_ctx();
+  if (!h) return fail(nullptr, GMPE_E_INVALID, "gmpe_create: out of host memory");
+  h->cfg = *cfg;
+  h->device = device;
+  h->launches = 0;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device);
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  h->threads = 256;
+  plan_tiles(h->cfg, h->threads, &h->wpb, &h->num_tiles);
+  const bool f64 = cfg->precision == GMPE_F64;
+  h->smem_bytes = f64 ? smem_for<double>(h->cfg, h->wpb) : smem_for<float>(h->cfg, h->wpb);
+  const void* fn = f64 ? (const void*)gmpe_step_kernel<double> : (const void*)gmpe_step_kernel<float>;
+  int max_optin = 0;
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (h->smem_bytes > (size_t)max_optin) {
+    std::string m = "gmpe_create: tile needs " + std::to_string(h->smem_bytes) + " B of shared memory, device allows " + std::to_string(max_optin);
+    delete h;
+    cudaSetDevice(prev);
+    return fail(nullptr, GMPE_E_INVALID, m);
+  }
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  int per_sm = 1;
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, h->threads, h->smem_bytes);
+  if (e != cudaSuccess) {
+    std::string m = std::string("gmpe_create: ") + cudaGetErrorString(e);
+    delete h;
+    cudaSetDevice(prev);
+    return fail(nullptr, GMPE_E_CUDA, m);
+  }
+  if (per_sm < 1) per_sm = 1;
+  // persistent grid: one wave of resident CTAs, tiles strided over it (148 SMs on B200)
+  int64_t g = (int64_t)h->sm_count * per_sm;
+  h->grid = (int)(h->num_tiles < g ? h->num_tiles : g);
+  cudaSetDevice(prev);
+  *out = h;
+  return GMPE_OK;
+}
+
+int gmpe_destroy(gmpe_handle h) {
+  if (!h) return GMPE_E_NULL;
+  delete h;
+  return GMPE_OK;
+}
+
+const char* gmpe_last_error(gmpe_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int64_t gmpe_launch_count(gmpe_handle h) { return h ? h->launches : 0; }
+
+static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* act, const uint8_t* mask,
+                  const GmpeStepInject* inj, const GmpeStepOut* out, void* stream) {
+  const GmpeConfig& c = h->cfg;
+  if (!st || !out) return fail(h, GMPE_E_NULL, "state / out struct is NULL");
+  if (!st->agent_state || !st->agent_aux || !st->agent_flags || !st->agent_cnt || !st->world_f || !st->world_i || !st->landmarks)
+    return fail(h, GMPE_E_NULL, "a required state array is NULL");
+  if ((c.num_obstacles && !st->obstacles) || (c.num_walls && !st->walls)) return fail(h, GMPE_E_NULL, "obstacles / walls array is NULL");
+  if (mode == MODE_STEP && (!act || !out->reward || !out->done)) return fail(h, GMPE_E_NULL, "gmpe_step needs action_idx, out.reward and out.done");
+  if ((c.flags & GMPE_FLAG_ENV_EDGES) && out->edge_index && (!out->edge_attr || !out->num_edges)) return fail(h, GMPE_E_NULL, "edge_attr / num_edges missing");
+  if ((c.flags & GMPE_FLAG_GNN_EDGES) && out->gnn_edge_index && (!out->gnn_edge_attr || !out->gnn_num_edges)) return fail(h, GMPE_E_NULL, "gnn_edge_attr / gnn_num_edges missing");
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  p.c = c;
+  p.st = *st;
+  p.out = *out;
+  p.act = act;
+  p.env_mask = mask;
+  p.theta = inj ? inj->theta_draw : nullptr;
+  p.has_rst = (inj && inj->reset_state) ? 1 : 0;
+  if (p.has_rst) p.rst = *inj->reset_state;
+  p.mode = mode;
+  p.wpb = h->wpb;
+  p.num_tiles = h->num_tiles;
+  const int N = c.num_agents, L = c.num_landmarks, O = c.num_obstacles, W = c.num_walls;
+  p.E = N + L + O + W;
+  p.F = c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
+  p.dN = FastDiv::make(N); p.dE = FastDiv::make(p.E); p.dL = FastDiv::make(L); p.dO = FastDiv::make(O);
+  p.dW = FastDiv::make(W); p.dF = FastDiv::make(p.F); p.d16 = FastDiv::make(16);
+  p.dE2 = FastDiv::make(p.E * 2); p.dNE2 = FastDiv::make(N * p.E * 2); p.dEE = FastDiv::make(p.E * p.E);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c.precision == GMPE_F64) gmpe_step_kernel<double><<<h->grid, h->threads, h->smem_bytes, s>>>(p);
+  else gmpe_step_kernel<float><<<h->grid, h->threads, h->smem_bytes, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (prev != h->device) cudaSetDevice(prev);
+  if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e));
+  h->launches += 1;
+  return GMPE_OK;
+}
+
+int gmpe_reset(gmpe_handle h, const GmpeState* st, const uint8_t* env_mask, const GmpeStepInject* inject,
+               const GmpeStepOut* out, void* cuda_stream) {
+  if (!h) return GMPE_E_NULL;
+  return launch(h, MODE_RESET, st, nullptr, env_mask, inject, out, cuda_stream);
+}
+
+int gmpe_step(gmpe_handle h, const GmpeState* st, const int32_t* action_idx, const GmpeStepInject* inject,
+              const GmpeStepOut* out, void* cuda_stream) {
+  if (!h) return GMPE_E_NULL;
+  return launch(h, MODE_STEP, st, action_idx, nullptr, inject, out, cuda_stream);
+}
+
+int gmpe_decode_onehot(gmpe_handle h, const void* onehot, int elem_bytes, int32_t* action_idx, void* cuda_stream) {
+  if (!h) return GMPE_E_NULL;
+  if (!onehot || !action_idx) return fail(h, GMPE_E_NULL, "gmpe_decode_onehot: NULL buffer");
+  if (elem_bytes != 4 && elem_bytes != 8) return fail(h, GMPE_E_INVALID, "gmpe_decode_onehot: elem_bytes must be 4 or 8");
+  const int64_t rows = (int64_t)h->cfg.num_worlds * h->cfg.num_agents;
+  const int A = h->cfg.total_actions;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const int threads = 256;
+  const int blocks = (int)((rows + threads - 1) / threads);
+  if (elem_bytes == 4) decode_onehot_kernel<float><<<blocks, threads, 0, s>>>((const float*)onehot, action_idx, rows, A);
+  else decode_onehot_kernel<double><<<blocks, threads, 0, s>>>((const double*)onehot, action_idx, rows, A);
+  cudaError_t e = cudaGetLastError();
+  if (prev != h->device) cudaSetDevice(prev);
+  if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("decode_onehot launch failed: ") + cudaGetErrorString(e));
+  h->launches += 1;
+  return GMPE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// gmpe_device.cuh -- small device-side building blocks of the GraphMPE step kernels:
+// Real traits (fp32 production / fp64 strict parity), Philox4x32-10, exact fast
+// division by launch-time constants, and the scalar math of the step path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gmpe.h"
+
+namespace gmpe {
+
+template <typename Real> struct RT;
+template <> struct RT<float> {
+  using V2 = float2;
+  using V4 = float4;
+  static __device__ __forceinline__ V2 mk2(float x, float y) { return make_float2(x, y); }
+  static __device__ __forceinline__ V4 mk4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
+};
+template <> struct RT<double> {
+  using V2 = double2;
+  using V4 = double4;
+  static __device__ __forceinline__ V2 mk2(double x, double y) { return make_double2(x, y); }
+  static __device__ __forceinline__ V4 mk4(double x, double y, double z, double w) { return make_double4(x, y, z, w); }
+};
+
+// ---- exact division by a launch-time constant d (d <= 2^12, n < 2^20) -------------
+struct FastDiv {
+  uint32_t mul, d;
+  __host__ static FastDiv make(uint32_t d) {
+    FastDiv f;
+    f.d = d ? d : 1;
+    f.mul = (uint32_t)((0x100000000ull + f.d - 1) / f.d);  // ceil(2^32 / d)
+    return f;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : __umulhi(n, mul); }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+
+// ---- Philox4x32-10, counter = (idx, episode, world_lo, world_hi), key = seed -------
+// Same specification as the CPU oracle (oracle/gmpe_oracle.c) so free-running batches
+// can be compared; the code is independent.
+__device__ __forceinline__ double philox_uniform01(uint64_t seed, int64_t world, uint32_t episode, uint32_t idx) {
+  uint32_t c0 = idx, c1 = episode, c2 = (uint32_t)world, c3 = (uint32_t)((uint64_t)world >> 32);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return ((double)(c0 >> 5) * 67108864.0 + (double)(c1 >> 6)) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ double philox_uniform(uint64_t seed, int64_t world, uint32_t ep, uint32_t idx, double lo, double hi) {
+  return lo + (hi - lo) * philox_uniform01(seed, world, ep, idx);
+}
+
+// ---- scalar math --------------------------------------------------------------------
+__device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+__device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+__device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+__device__ __forceinline__ double abs_(double x) { return fabs(x); }
+__device__ __forceinline__ void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ float asin_(float x) { return asinf(x); }
+__device__ __forceinline__ double asin_(double x) { return asin(x); }
+__device__ __forceinline__ float exp_(float x) { return expf(x); }
+__device__ __forceinline__ double exp_(double x) { return exp(x); }
+__device__ __forceinline__ float log1p_(float x) { return log1pf(x); }
+__device__ __forceinline__ double log1p_(double x) { return log1p(x); }
+__device__ __forceinline__ bool isnan_(float x) { return isnan(x); }
+__device__ __forceinline__ bool isnan_(double x) { return isnan(x); }
+
+// np.linalg.norm of a 2-vector; one definition for every distance so that adjacency,
+// edges and collision tests see identical values.
+template <typename Real>
+__device__ __forceinline__ Real norm2(Real x, Real y) { return sqrt_(x * x + y * y); }
+
+template <typename Real>
+__device__ __forceinline__ Real clip(Real v, Real lo, Real hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// np.logaddexp(0, x)
+template <typename Real>
+__device__ __forceinline__ Real softplus(Real x) {
+  return x > Real(0) ? x + log1p_(exp_(-x)) : log1p_(exp_(x));
+}
+
+// the reference casts positions to float32 before projecting on the tube frame (july:624)
+__device__ __forceinline__ float trunc32(float x) { return x; }
+__device__ __forceinline__ double trunc32(double x) { return (double)(float)x; }
+
+// fp32 production keeps headings wrapped to [-pi, pi) (the reference never
+// wraps theta, which costs fp32 ulps); fp64 strict parity leaves theta raw.
+__device__ __forceinline__ float wrap_heading(float th) {
+  const float two_pi = 6.283185307179586f, inv = 0.15915494309189535f;
+  return th - two_pi * rintf(th * inv);
+}
+__device__ __forceinline__ double wrap_heading(double th) { return th; }
+
+}  // namespace gmpe

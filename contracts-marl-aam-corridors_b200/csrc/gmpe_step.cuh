@@ -1,0 +1,939 @@
+// gmpe_step.cuh -- the fused GraphMPE step kernel (sm_100a).
+//
+// One launch advances every world of the batch by one environment step and emits every
+// tensor the reference's MultiAgentGraphEnv.step returns (multiagent/environment.py:
+// 1021-1063), plus the auto-reset of graphworker (onpolicy/envs/env_wrappers.py:861-873).
+//
+// Mapping.  A CTA owns a tile of WPB consecutive worlds.  State is world-major
+// ([B][N][4] etc.), so in phase A "thread = (world, agent)" reads and writes it with
+// perfectly coalesced 128-bit accesses; entity state of the tile is staged in shared
+// memory and every pairwise term (collision forces, collision penalties, neighbour
+// selection, adjacency) is computed from there.  The reference evaluates agents in index
+// order with in-place side effects; the kernel reproduces that exactly with
+// a two-pass formulation: pass A computes what depends on an agent's own state only
+// (phase machine, goal reach, heading re-draw), pass B evaluates agent j against
+// post-reward values of agents < j and pre-reward values of agents > j.
+// In phase B all threads of the CTA generate the output tensors element-parallel from
+// shared memory, so that global stores are contiguous 128-bit vectors across the tile
+// (obs is staged, node_obs / adj are generated in place, edges are stream-compacted per
+// world with warp ballot + popc into the fixed-capacity padded buffers).
+//
+// The path is bandwidth / latency bound: no tensor cores by design.
+#pragma once
+#include <type_traits>
+
+#include "gmpe_device.cuh"
+
+namespace gmpe {
+
+enum { MODE_STEP = 0, MODE_RESET = 1 };
+
+struct KParams {
+  GmpeConfig c;
+  GmpeState st;
+  GmpeStepOut out;
+  GmpeState rst;  // injected reset state (valid when has_rst)
+  const int32_t* act;
+  const void* theta;
+  const uint8_t* env_mask;
+  int has_rst;
+  int mode;
+  int wpb;        // worlds per tile
+  int num_tiles;
+  int E, F;       // entities per world, obs width
+  FastDiv dN, dE, dL, dO, dW, dF, d16, dE2, dNE2, dEE;
+};
+
+// ---- shared memory carve-up --------------------------------------------------------
+template <typename Real>
+struct Smem {
+  typename RT<Real>::V2* pos;      // [WPB*E]   post-step positions of every entity
+  typename RT<Real>::V2* velpre;   // [WPB*N]   p_vel before reward()
+  typename RT<Real>::V2* velpost;  // [WPB*N]   p_vel after reward() (heading re-draw on goal reach)
+  typename RT<Real>::V4* nst;      // [WPB*N]   reset: freshly placed agent states
+  Real* wf;                        // [WPB*16]
+  Real* wl;                        // [WPB*W*4]
+  Real* obs;                       // [WPB*N*F] staging
+  Real* rew;                       // [WPB*N]
+  Real* sperr;                     // [WPB*N]
+  int32_t* cold;                   // [WPB*N*3] info counters before this step
+  int32_t* cnew;                   // [WPB*N*3] ... after
+  int32_t* wstep;                  // [WPB]
+  int32_t* wep;                    // [WPB]
+  uint8_t* stpre;                  // [WPB*N]
+  uint8_t* stpost;                 // [WPB*N]
+  uint8_t* done;                   // [WPB*N]
+  uint8_t* wreset;                 // [WPB]
+  uint8_t* wwrite;                 // [WPB]
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename Real>
+__host__ __device__ inline size_t smem_layout(int wpb, int N, int E, int W, int F, Smem<Real>* s, unsigned char* base) {
+  size_t o = 0;
+  auto take = [&](size_t bytes, size_t al) { o = align_up(o, al); size_t r = o; o += bytes; return r; };
+  size_t R = sizeof(Real);
+  size_t o_pos = take(2 * R * wpb * E, 16);
+  size_t o_vpre = take(2 * R * wpb * N, 16);
+  size_t o_vpost = take(2 * R * wpb * N, 16);
+  size_t o_nst = take(4 * R * wpb * N, 32);
+  size_t o_wf = take(R * wpb * GMPE_WORLD_F, 16);
+  size_t o_wl = take(R * wpb * (W > 0 ? W : 1) * GMPE_WALL_F, 16);
+  size_t o_obs = take(R * wpb * N * F, 16);
+  size_t o_rew = take(R * wpb * N, 16);
+  size_t o_sp = take(R * wpb * N, 16);
+  size_t o_cold = take(4 * wpb * N * 3, 16);
+  size_t o_cnew = take(4 * wpb * N * 3, 16);
+  size_t o_wstep = take(4 * wpb, 16);
+  size_t o_wep = take(4 * wpb, 16);
+  size_t o_stpre = take(wpb * N, 16);
+  size_t o_stpost = take(wpb * N, 16);
+  size_t o_done = take(wpb * N, 16);
+  size_t o_wreset = take(wpb, 16);
+  size_t o_wwrite = take(wpb, 16);
+  if (s) {
+    s->pos = (typename RT<Real>::V2*)(base + o_pos);
+    s->velpre = (typename RT<Real>::V2*)(base + o_vpre);
+    s->velpost = (typename RT<Real>::V2*)(base + o_vpost);
+    s->nst = (typename RT<Real>::V4*)(base + o_nst);
+    s->wf = (Real*)(base + o_wf);
+    s->wl = (Real*)(base + o_wl);
+    s->obs = (Real*)(base + o_obs);
+    s->rew = (Real*)(base + o_rew);
+    s->sperr = (Real*)(base + o_sp);
+    s->cold = (int32_t*)(base + o_cold);
+    s->cnew = (int32_t*)(base + o_cnew);
+    s->wstep = (int32_t*)(base + o_wstep);
+    s->wep = (int32_t*)(base + o_wep);
+    s->stpre = base + o_stpre;
+    s->stpost = base + o_stpost;
+    s->done = base + o_done;
+    s->wreset = base + o_wreset;
+    s->wwrite = base + o_wwrite;
+  }
+  return align_up(o, 16);
+}
+
+// ---- per-agent pieces --------------------------------------------------------------
+
+// MultiAgentBaseEnv._set_action (environment.py:336-475), index form of the one-hot
+template <typename Real>
+__device__ __forceinline__ void decode_action(const GmpeConfig& c, int a, Real& u0, Real& u1) {
+  double x = 0.0, y = 0.0;
+  if (c.dynamics == GMPE_DYN_DOUBLE_INTEGRATOR) {
+    if (c.total_actions == 9) {  // environment.py:382-392
+      const double d = 0.71;
+      switch (a) {
+        case 1: x = -1; break;
+        case 2: x = -d; y = -d; break;
+        case 3: y = -1; break;
+        case 4: x = d; y = -d; break;
+        case 5: x = 1; break;
+        case 6: x = d; y = d; break;
+        case 7: y = 1; break;
+        case 8: x = -d; y = d; break;
+        default: break;
+      }
+    } else {  // environment.py:404-406
+      x = (double)((a == 1) - (a == 2));
+      y = (double)((a == 3) - (a == 4));
+    }
+  } else {  // environment.py:424-449; np.linspace(start, stop, 5)[k] = k*step + start, last = stop
+    int ar = a / 5, ac = a - ar * 5;
+    double ws = (2.0 * c.ang_rate_max) / 4.0, as = (c.accel_max - c.accel_min) / 4.0;
+    x = ar == 4 ? c.ang_rate_max : (double)ar * ws + (-c.ang_rate_max);
+    y = ac == 4 ? c.accel_max : (double)ac * as + c.accel_min;
+  }
+  u0 = Real(x * c.sensitivity);  // environment.py:460-463
+  u1 = Real(y * c.sensitivity);
+}
+
+// Closed form of solve_ivp(RK45) over [0, dt] (core.py:125-139, 207-218, 300-316),
+// then the speed clamp and the travelled-distance counter.
+template <typename Real>
+__device__ __forceinline__ void integrate_kinematic(const GmpeConfig& c, typename RT<Real>::V4& s, Real u0, Real u1, Real& p_dist) {
+  const Real dt = Real(c.dt);
+  if (c.dynamics == GMPE_DYN_DOUBLE_INTEGRATOR) {
+    s.x += s.z * dt + Real(0.5) * u0 * dt * dt;
+    s.y += s.w * dt + Real(0.5) * u1 * dt * dt;
+    s.z += u0 * dt;
+    s.w += u1 * dt;
+    Real speed = sqrt_(s.z * s.z + s.w * s.w);
+    const Real vmax = Real(c.v_max);
+    if (speed > vmax) {  // core.py:213-215
+      s.z = vmax * s.z / speed;
+      s.w = vmax * s.w / speed;
+      speed = sqrt_(s.z * s.z + s.w * s.w);
+    }
+    p_dist += speed * dt;
+    return;
+  }
+  Real th = s.z, v = s.w;
+  Real th1 = th + u0 * dt, v1 = v + u1 * dt;
+  Real s0, c0;
+  sincos_(th, &s0, &c0);
+  if (u0 != Real(0)) {
+    Real s1, c1;
+    sincos_(th1, &s1, &c1);
+    Real iw = Real(1) / u0;
+    s.x += (v1 * s1 - v * s0) * iw + u1 * (c1 - c0) * iw * iw;
+    s.y += -(v1 * c1 - v * c0) * iw + u1 * (s1 - s0) * iw * iw;
+  } else {
+    Real d = v * dt + Real(0.5) * u1 * dt * dt;
+    s.x += c0 * d;
+    s.y += s0 * d;
+  }
+  v1 = clip(v1, Real(c.v_min), Real(c.v_max));  // core.py:132-135, 309-312
+  s.z = wrap_heading(th1);
+  s.w = v1;
+  p_dist += v1 * dt;
+}
+
+// get_agent_phase (july:683-733) with _tube_coords / _in_tube_rect / _in_entrance_gate
+// (july:621-637).  pp is agent.previous_phase and may be promoted to 2 (july:727).
+template <typename Real>
+__device__ __forceinline__ int tube_phase(const Real* wf, Real px, Real py, int& pp) {
+  const Real eps = Real(0.05);
+  Real rx = trunc32(px) - wf[GMPE_WF_ENT_X], ry = trunc32(py) - wf[GMPE_WF_ENT_Y];
+  Real s = rx * wf[GMPE_WF_E_X] + ry * wf[GMPE_WF_E_Y];
+  Real y = rx * wf[GMPE_WF_N_X] + ry * wf[GMPE_WF_N_Y];
+  Real L = wf[GMPE_WF_L], hw = wf[GMPE_WF_HALF_W];
+  bool lat = abs_(y) <= hw + eps;
+  bool in_tube = (-eps <= s) && (s <= L + eps) && lat;
+  Real tdx = wf[GMPE_WF_EXIT_X] - wf[GMPE_WF_ENT_X], tdy = wf[GMPE_WF_EXIT_Y] - wf[GMPE_WF_ENT_Y];
+  Real tn = norm2(tdx, tdy);
+  tdx /= tn; tdy /= tn;
+  bool passed = ((px - wf[GMPE_WF_EXIT_X]) * tdx + (py - wf[GMPE_WF_EXIT_Y]) * tdy) > Real(0);
+  Real gf = Real(0.08) * L, gb = Real(0.02) * L;
+  bool gate = (-gb - eps <= s) && (s <= gf + eps) && lat;
+  if (!in_tube && !passed) return 0;
+  if (in_tube) return pp == 0 ? (gate ? 1 : 0) : 1;
+  if (pp == 1) { pp = 2; return 2; }  // here passed is true
+  if (pp == 2) return 2;
+  return 0;
+}
+
+// is_obstacle_collision (july:864-890): obstacles within 2*(size_o + size), walls as a
+// 1.5*size band around the segment.
+template <typename Real>
+__device__ __forceinline__ bool obstacle_collision(const GmpeConfig& c, const typename RT<Real>::V2* pos_w, const Real* wl_w,
+                                                   int N, int L, int O, int W, Real px, Real py) {
+  const Real size = Real(c.entity_size);
+  const Real dmin = Real(2.0) * (size + size);
+  for (int o = 0; o < O; ++o) {
+    typename RT<Real>::V2 q = pos_w[N + L + o];
+    if (norm2(q.x - px, q.y - py) < dmin) return true;
+  }
+  const Real band = Real(1.5) * size;
+  for (int q = 0; q < W; ++q) {
+    const Real* w = wl_w + q * GMPE_WALL_F;
+    Real pa = w[0] == Real(0) ? py : px;  // coordinate along the wall's axis position
+    Real pl = w[0] == Real(0) ? px : py;
+    if (w[1] - band <= pa && pa <= w[1] + band && w[2] - band <= pl && pl <= w[3] + band) return true;
+  }
+  return false;
+}
+
+// get_wall_collision_force (core.py:909-964)
+template <typename Real>
+__device__ __forceinline__ void wall_force(const GmpeConfig& c, const Real* w, Real px, Real py, Real& fx, Real& fy) {
+  const Real size = Real(c.entity_size);
+  bool horiz = w[0] == Real(0);
+  Real ppar = horiz ? px : py, pperp = horiz ? py : px;
+  if (ppar < w[2] - size || ppar > w[3] + size) return;
+  Real st = Real(0), ct = Real(1), dist_min;
+  if (ppar < w[2] || ppar > w[3]) {
+    Real past = ppar < w[2] ? ppar - w[2] : ppar - w[3];
+    Real theta = asin_(past / size);
+    sincos_(theta, &st, &ct);
+    dist_min = ct * size + Real(0.5) * Real(c.wall_width);
+  } else {
+    dist_min = size + Real(0.5) * Real(c.wall_width);
+  }
+  Real delta = pperp - w[1];
+  Real dist = abs_(delta);
+  bool classic = (c.flags & GMPE_FLAG_CLASSIC_CONTACT) != 0;
+  Real k = Real(classic ? c.contact_margin : c.wall_contact_margin);
+  Real cf = Real(classic ? c.contact_force : c.wall_contact_force);
+  Real pen = softplus(-(dist - dist_min) / k) * k;
+  Real fm = cf * delta / dist * pen;
+  Real fperp = ct * fm, fpar = st * abs_(fm);
+  if (horiz) { fx += fpar; fy += fperp; } else { fx += fperp; fy += fpar; }
+}
+
+// Scenario.observation (july:1337-1463) into the staging row o[19]
+template <typename Real>
+__device__ __forceinline__ void july_obs(const typename RT<Real>::V2* pos_w, const Real* wf, int N, int i,
+                                         Real vx, Real vy, int phase, Real* o) {
+  typename RT<Real>::V2 p = pos_w[i], g = pos_w[N + i];  // goal_match_index = arange (july:356)
+  Real d1 = Real(0), d2 = Real(0);
+  typename RT<Real>::V2 r1 = RT<Real>::mk2(0, 0), r2 = RT<Real>::mk2(0, 0);
+  int cnt = 0;
+  for (int k = 0; k < N; ++k) {  // two nearest others, stable on ties (july:1399-1415)
+    if (k == i) continue;
+    typename RT<Real>::V2 q = pos_w[k];
+    Real rx = q.x - p.x, ry = q.y - p.y, d = norm2(rx, ry);
+    if (cnt == 0 || d < d1) { d2 = d1; r2 = r1; d1 = d; r1 = RT<Real>::mk2(rx, ry); }
+    else if (cnt == 1 || d < d2) { d2 = d; r2 = RT<Real>::mk2(rx, ry); }
+    ++cnt;
+  }
+  Real gx = g.x - p.x, gy = g.y - p.y;
+  o[0] = p.x; o[1] = p.y; o[2] = vx; o[3] = vy;
+  o[4] = gx; o[5] = gy; o[6] = Real(0); o[7] = gx; o[8] = gy;
+  o[9] = r1.x; o[10] = r1.y; o[11] = r2.x; o[12] = r2.y;
+  o[13] = wf[GMPE_WF_ENT_X] - p.x; o[14] = wf[GMPE_WF_ENT_Y] - p.y;
+  o[15] = wf[GMPE_WF_EXIT_X] - p.x; o[16] = wf[GMPE_WF_EXIT_Y] - p.y;
+  o[17] = wf[GMPE_WF_WIDTH];
+  o[18] = Real(phase);
+}
+
+// ---- reset (thread 0 of a world): random_scenario + setup_tube_params (july:440-613),
+// set_landmarks_in_point (utils.py:165-193); nav placement is defined-by-build
+template <typename Real>
+__device__ void place_world(const KParams& p, const Smem<Real>& sm, int lw, int64_t b) {
+  const GmpeConfig& c = p.c;
+  const int N = c.num_agents, L = c.num_landmarks, O = c.num_obstacles, W = c.num_walls, E = p.E;
+  typename RT<Real>::V2* pos_w = sm.pos + lw * E;
+  typename RT<Real>::V4* nst = sm.nst + lw * N;
+  Real* wf = sm.wf + lw * GMPE_WORLD_F;
+  Real* wl = sm.wl + lw * W * GMPE_WALL_F;
+  const uint64_t seed = c.seed;
+  const int64_t gw = c.world_offset + b;
+  const uint32_t ep = (uint32_t)sm.wep[lw];
+  uint32_t idx = 0;
+  const double ws = c.world_size;
+  const bool heading = c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR;
+  const Real sep = Real(c.separation_dist);
+  if (c.scenario == GMPE_SCEN_JULY_TUBE) {
+    (void)philox_uniform01(seed, gw, ep, idx++);  // wall_length draw (july:368), value unused
+    double width = fmax(3 * c.entity_size * 2.5, ws * 0.15);
+    double angle = philox_uniform(seed, gw, ep, idx++, -1.5707963267948966, 1.5707963267948966);
+    double tl = ws * 0.8, ca, sa;
+    sincos(angle, &sa, &ca);
+    double ent0 = sa * (tl / 4), ent1 = ca * (tl / 4), ext0 = sa * (-tl / 4), ext1 = ca * (-tl / 4);
+    double Lh = sqrt((ext0 - ent0) * (ext0 - ent0) + (ext1 - ent1) * (ext1 - ent1)) + 1e-9;
+    double e0 = (ext0 - ent0) / Lh, e1 = (ext1 - ent1) / Lh;
+    wf[GMPE_WF_ENT_X] = Real(ent0); wf[GMPE_WF_ENT_Y] = Real(ent1);
+    wf[GMPE_WF_EXIT_X] = Real(ext0); wf[GMPE_WF_EXIT_Y] = Real(ext1);
+    wf[GMPE_WF_E_X] = Real(e0); wf[GMPE_WF_E_Y] = Real(e1);
+    wf[GMPE_WF_N_X] = Real((float)(-e1)); wf[GMPE_WF_N_Y] = Real((float)e0);
+    wf[GMPE_WF_L] = Real(Lh); wf[GMPE_WF_HALF_W] = Real(width * 0.5);
+    wf[GMPE_WF_WIDTH] = Real(width); wf[GMPE_WF_ANGLE] = Real(angle);
+    int k = 0;
+    while (k < N) {  // july:452-486
+      double jx = 0.2 * philox_uniform(seed, gw, ep, idx, -ws, ws);
+      double jy = 0.2 * philox_uniform(seed, gw, ep, idx + 1, -ws, ws);
+      idx += 2;
+      double d = (ws + k) / 5;
+      Real px = Real(ent0 + d * sa + jx), py = Real(ent1 + d * ca + jy);
+      bool bad = obstacle_collision<Real>(c, pos_w, wl, N, L, O, W, px, py);
+      for (int a = 0; a < k && !bad; ++a) bad = norm2(nst[a].x - px, nst[a].y - py) < sep;
+      if (bad) continue;
+      Real th = Real(0), v = Real(0);
+      if (heading) { th = wrap_heading(Real(philox_uniform(seed, gw, ep, idx++, 0.0, 6.283185307179586))); v = Real(c.v_min); }
+      nst[k] = RT<Real>::mk4(px, py, th, v);
+      ++k;
+    }
+    for (int l = 0; l < L; ++l) pos_w[N + l] = RT<Real>::mk2(Real(ext0 + sa * (-ws / 3)), Real(ext1 + ca * (-ws / 3)));
+  } else {
+    const double h = ws / 2;
+    for (int q = 0; q < W; ++q) {  // boundary box: H top, H bottom, V right, V left
+      Real* w = wl + q * GMPE_WALL_F;
+      w[0] = (q & 2) ? Real(1) : Real(0);
+      w[1] = Real((q & 1) ? -h : h);
+      w[2] = Real(-h); w[3] = Real(h);
+      Real mid = Real(0.5) * (w[2] + w[3]);
+      pos_w[N + L + O + q] = w[0] == Real(0) ? RT<Real>::mk2(mid, w[1]) : RT<Real>::mk2(w[1], mid);
+    }
+    for (int o = 0; o < O; ++o) {
+      pos_w[N + L + o] = RT<Real>::mk2(Real(0.9 * philox_uniform(seed, gw, ep, idx, -h, h)),
+                                       Real(0.9 * philox_uniform(seed, gw, ep, idx + 1, -h, h)));
+      idx += 2;
+    }
+    int k = 0;
+    while (k < N) {
+      Real px = Real(0.9 * philox_uniform(seed, gw, ep, idx, -h, h)), py = Real(0.9 * philox_uniform(seed, gw, ep, idx + 1, -h, h));
+      idx += 2;
+      bool bad = obstacle_collision<Real>(c, pos_w, wl, N, L, O, W, px, py);
+      for (int a = 0; a < k && !bad; ++a) bad = norm2(nst[a].x - px, nst[a].y - py) < sep;
+      if (bad) continue;
+      Real th = Real(0), v = Real(0);
+      if (heading) { th = wrap_heading(Real(philox_uniform(seed, gw, ep, idx++, 0.0, 6.283185307179586))); v = Real(c.v_min); }
+      nst[k] = RT<Real>::mk4(px, py, th, v);
+      ++k;
+    }
+    const Real lmin = Real(1.2 * (2 * c.entity_size));  // is_landmark_collision july:916-925
+    k = 0;
+    while (k < L) {
+      Real px = Real(0.9 * philox_uniform(seed, gw, ep, idx, -h, h)), py = Real(0.9 * philox_uniform(seed, gw, ep, idx + 1, -h, h));
+      idx += 2;
+      bool bad = obstacle_collision<Real>(c, pos_w, wl, N, L, O, W, px, py);
+      for (int a = 0; a < k && !bad; ++a) bad = norm2(pos_w[N + a].x - px, pos_w[N + a].y - py) < lmin;
+      if (bad) continue;
+      pos_w[N + k] = RT<Real>::mk2(px, py);
+      ++k;
+    }
+  }
+}
+
+// ---- the kernel ----------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(256) gmpe_step_kernel(const __grid_constant__ KParams p) {
+  using V2 = typename RT<Real>::V2;
+  using V4 = typename RT<Real>::V4;
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  const GmpeConfig& c = p.c;
+  const int N = c.num_agents, L = c.num_landmarks, O = c.num_obstacles, W = c.num_walls, E = p.E, F = p.F;
+  const int B = c.num_worlds, WPB = p.wpb;
+  const bool july = c.scenario == GMPE_SCEN_JULY_TUBE;
+  const bool heading = c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR;
+  const bool do_info = (c.flags & GMPE_FLAG_INFO) != 0;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  Smem<Real> sm;
+  smem_layout<Real>(WPB, N, E, W, F, &sm, smem_raw);
+
+  Real* g_as = (Real*)p.st.agent_state;
+  Real* g_aux = (Real*)p.st.agent_aux;
+  uint32_t* g_fl = (uint32_t*)p.st.agent_flags;
+  int32_t* g_cnt = p.st.agent_cnt;
+  Real* g_wf = (Real*)p.st.world_f;
+  int32_t* g_wi = p.st.world_i;
+  Real* g_lm = (Real*)p.st.landmarks;
+  Real* g_ob = (Real*)p.st.obstacles;
+  Real* g_wl = (Real*)p.st.walls;
+
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int w0 = tile * WPB;
+    const int nw = min(WPB, B - w0);
+    // ---------------- cooperative, coalesced loads of world-level state -------------
+    for (int q = tid; q < nw * GMPE_WORLD_F; q += nthr) sm.wf[q] = g_wf[(size_t)w0 * GMPE_WORLD_F + q];
+    for (int q = tid; q < nw * L; q += nthr) {
+      uint32_t lw, l; p.dL.divmod(q, lw, l);
+      sm.pos[lw * E + N + l] = ((const V2*)g_lm)[(size_t)w0 * L + q];
+    }
+    for (int q = tid; q < nw * O; q += nthr) {
+      uint32_t lw, o; p.dO.divmod(q, lw, o);
+      sm.pos[lw * E + N + L + o] = ((const V2*)g_ob)[(size_t)w0 * O + q];
+    }
+    for (int q = tid; q < nw * W; q += nthr) {
+      uint32_t lw, k; p.dW.divmod(q, lw, k);
+      const Real* src = g_wl + ((size_t)w0 * W + q) * GMPE_WALL_F;
+      Real* dst = sm.wl + q * GMPE_WALL_F;
+      Real o0 = src[0], a = src[1], e0 = src[2], e1 = src[3];
+      dst[0] = o0; dst[1] = a; dst[2] = e0; dst[3] = e1;
+      Real mid = Real(0.5) * (e0 + e1);  // wall "position" = segment midpoint
+      sm.pos[lw * E + N + L + O + k] = o0 == Real(0) ? RT<Real>::mk2(mid, a) : RT<Real>::mk2(a, mid);
+    }
+    for (int q = tid; q < nw; q += nthr) {
+      int32_t stp = g_wi[(size_t)(w0 + q) * GMPE_WORLD_I + GMPE_WI_STEP];
+      sm.wstep[q] = p.mode == MODE_STEP ? stp + 1 : stp;  // environment.py:1024
+      sm.wep[q] = g_wi[(size_t)(w0 + q) * GMPE_WORLD_I + GMPE_WI_EPISODE];
+      uint8_t m = p.mode == MODE_STEP ? 1 : (p.env_mask ? (p.env_mask[w0 + q] != 0) : 1);
+      sm.wwrite[q] = m;
+      sm.wreset[q] = p.mode == MODE_STEP ? 0 : m;
+    }
+
+    // ---------------- phase A: thread = (world, agent) -------------------------------
+    const bool active = tid < nw * N;
+    uint32_t lw = 0, i = 0;
+    if (active) p.dN.divmod(tid, lw, i);
+    const int64_t b = w0 + (int64_t)lw;
+    const size_t ga = (size_t)w0 * N + tid;  // global agent slot
+    V4 s = RT<Real>::mk4(0, 0, 0, 0);
+    V2 aux = RT<Real>::mk2(0, 0);
+    uint32_t flw = 0;
+    Real u0 = Real(0), u1 = Real(0);
+    int st_pre = 0, pp = 0, phase_reached = 0, goal_reached = 0;
+    if (active) {
+      s = ((const V4*)g_as)[ga];
+      aux = ((const V2*)g_aux)[ga];
+      flw = g_fl[ga];
+      st_pre = flw & 0xff; pp = (flw >> 8) & 0xff; phase_reached = (flw >> 16) & 0xff; goal_reached = (flw >> 24) & 0xff;
+    }
+    V2 vpre = RT<Real>::mk2(0, 0), vpost = RT<Real>::mk2(0, 0);
+    Real hx = Real(1), hy = Real(0);  // heading_vec of the PRE-reward state (july:1130-1131)
+    int st_post = st_pre, ph = 0, pp_eff = pp;
+    bool reach = false;
+    Real d_goal = Real(0), rew = Real(0);
+    int done = 0;
+    const Real* wfw = sm.wf + lw * GMPE_WORLD_F;
+    V2* pos_w = sm.pos + lw * E;
+    const Real* wl_w = sm.wl + lw * W * GMPE_WALL_F;
+
+    if (p.mode == MODE_STEP) {
+      if (active) decode_action<Real>(c, p.act[ga], u0, u1);
+      if (c.physics == GMPE_PHYS_FORCE) {
+        // classic step order (onpolicy/envs/mpe/core.py:183-202) with the force functions of
+        // multiagent/core.py:766-984: positions first, then pairwise penetration forces
+        if (active) { pos_w[i] = RT<Real>::mk2(s.x, s.y); sm.stpre[tid] = (uint8_t)st_pre; }
+        __syncthreads();
+        if (active) {
+          const bool classic = (c.flags & GMPE_FLAG_CLASSIC_CONTACT) != 0;
+          const bool quirk = (c.flags & GMPE_FLAG_WALL_POINT_QUIRK) != 0;
+          Real fx = u0, fy = u1;  // apply_action_force: mass 1, accel None, no noise
+          const Real km = Real(c.contact_margin), cf = Real(c.contact_force);
+          const int kend = quirk ? E : N + L + O;
+          for (int k = 0; k < kend; ++k) {
+            if (k == (int)i || (k >= N && k < N + L)) continue;  // landmarks do not collide (july:298)
+            if (k < N && !classic && st_pre) continue;           // core.py:899: no agent-agent force on a done entity
+            V2 q = pos_w[k];
+            Real dx = s.x - q.x, dy = s.y - q.y, dist = norm2(dx, dy);
+            Real size_k = k >= N + L + O ? Real(c.wall_width) : Real(c.entity_size);
+            Real dmin = classic ? Real(c.entity_size) + size_k : Real(c.separation_dist);
+            Real pen = softplus(-(dist - dmin) / km) * km;
+            fx = cf * dx / dist * pen + fx;
+            fy = cf * dy / dist * pen + fy;
+          }
+          for (int q = 0; q < W; ++q) wall_force<Real>(c, wl_w + q * GMPE_WALL_F, s.x, s.y, fx, fy);
+          if (classic || !st_pre) {  // integrate_state core.py:827-845; done agents freeze
+            const Real dt = Real(c.dt);
+            s.z = s.z * Real(1 - c.damping) + fx * dt;
+            s.w = s.w * Real(1 - c.damping) + fy * dt;
+            if (c.max_speed > 0) {
+              Real speed = sqrt_(s.z * s.z + s.w * s.w);
+              if (speed > Real(c.max_speed)) { s.z = s.z / speed * Real(c.max_speed); s.w = s.w / speed * Real(c.max_speed); }
+            }
+            s.x += s.z * dt; s.y += s.w * dt;
+            aux.x += norm2(s.z * dt, s.w * dt);
+          }
+        }
+        __syncthreads();
+      } else if (active && !st_pre) {  // core.py:819-826
+        integrate_kinematic<Real>(c, s, u0, u1, aux.x);
+      }
+      if (active) {
+        if (heading) { sincos_(s.z, &hy, &hx); vpre = RT<Real>::mk2(s.w * hx, s.w * hy); }
+        else {
+          vpre = RT<Real>::mk2(s.z, s.w);
+          Real sp = norm2(s.z, s.w);  // DoubleIntegratorXYState.theta = arctan2(vy, vx), core.py:188-189
+          if (sp > Real(0)) { hx = s.z / sp; hy = s.w / sp; }
+        }
+        pos_w[i] = RT<Real>::mk2(s.x, s.y);
+        sm.velpre[tid] = vpre;
+        sm.stpre[tid] = (uint8_t)st_pre;
+      }
+    }
+    __syncthreads();  // world frame, static entities and post-step agent positions are in smem
+
+    if (p.mode == MODE_STEP && active) {
+      // ---- pass A: everything reward() derives from the agent's own state -----------
+      V2 g = pos_w[N + i];
+      d_goal = norm2(s.x - g.x, s.y - g.y);
+      if (july) {
+        ph = tube_phase<Real>(wfw, s.x, s.y, pp_eff);  // observation-time call may promote pp (july:727)
+        reach = (ph == 2) && (phase_reached != 0) && (d_goal < Real(c.goal_dist_thresh)) && !st_pre;
+      } else {
+        reach = (d_goal < Real(c.goal_dist_thresh)) && (c.flags & GMPE_FLAG_USE_DONES) && !st_pre;
+      }
+      vpost = vpre;
+      if (reach) {  // agent.status = True; state.reset_velocity() (july:1188-1190, core.py:324-333)
+        st_post = 1;
+        if (heading) {
+          if (july) {
+            Real th = p.theta ? ((const Real*)p.theta)[ga] : Real(NAN);
+            if (isnan_(th))
+              th = Real(philox_uniform(c.seed, c.world_offset + b, (uint32_t)sm.wep[lw],
+                                       (1u << 30) + (uint32_t)sm.wstep[lw] * 64u + i, 0.0, 6.283185307179586));
+            s.z = wrap_heading(th);
+          }
+          s.w = Real(c.v_min);
+          Real sn, cs; sincos_(s.z, &sn, &cs);
+          vpost = RT<Real>::mk2(s.w * cs, s.w * sn);
+        } else { s.z = Real(0); s.w = Real(0); vpost = RT<Real>::mk2(0, 0); }
+      }
+      sm.stpost[tid] = (uint8_t)st_post;
+      sm.velpost[tid] = vpost;
+    }
+    __syncthreads();
+
+    Real sp_err = Real(0);
+    int32_t cnt[GMPE_AGENT_CNT];
+    if (p.mode == MODE_STEP && active) {
+      // ---- pass B: terms that look at other agents (ordered semantics) ----
+      const uint8_t* spre = sm.stpre + lw * N;
+      const uint8_t* spost = sm.stpost + lw * N;
+      const Real sep = Real(c.separation_dist);
+      const Real coll = Real(c.collision_rew), goal = Real(c.goal_rew);
+      int ncoll_rew = 0, ncoll_info = 0;
+      int front = -1, back = -1;
+      Real fproj = Real(0), bproj = Real(0), fdist = Real(0), bdist = Real(0);
+      for (int k = 0; k < N; ++k) {
+        if (k == (int)i) continue;
+        V2 q = pos_w[k];
+        Real rx = q.x - s.x, ry = q.y - s.y, d = norm2(rx, ry);
+        int st_k = k < (int)i ? spost[k] : spre[k];
+        bool close = d < sep;
+        ncoll_rew += (close && !st_k && !st_pre);    // is_collision at reward(i) time (july:907-914)
+        ncoll_info += (close && !st_k && !st_post);  // ... at info_callback(i) time (july:785)
+        if (july) {  // front / back neighbours along the own heading (july:1136-1143)
+          Real proj = rx * hx + ry * hy;
+          if (proj > Real(0)) { if (front < 0 || proj < fproj) { front = k; fproj = proj; fdist = d; } }
+          else { if (back < 0 || proj > bproj) { back = k; bproj = proj; bdist = d; } }
+        }
+      }
+      bool obst = obstacle_collision<Real>(c, pos_w, wl_w, N, L, O, W, s.x, s.y);
+      if (do_info) {
+        const int32_t* gc = g_cnt + ga * GMPE_AGENT_CNT;
+#pragma unroll
+        for (int q = 0; q < GMPE_AGENT_CNT; ++q) cnt[q] = gc[q];
+        sm.cold[tid * 3 + 0] = cnt[GMPE_AC_DIST_TRAV_I];
+        sm.cold[tid * 3 + 1] = cnt[GMPE_AC_TIME_REQ_I];
+        sm.cold[tid * 3 + 2] = cnt[GMPE_AC_SPACING_VIOL];
+      } else {
+#pragma unroll
+        for (int q = 0; q < GMPE_AGENT_CNT; ++q) cnt[q] = 0;
+      }
+      int cur = ph;
+      if (july) {
+        rew -= Real(ncoll_rew) * (coll * Real(4));
+        if (obst) rew -= coll * Real(3);
+        Real tdx = wfw[GMPE_WF_EXIT_X] - wfw[GMPE_WF_ENT_X], tdy = wfw[GMPE_WF_EXIT_Y] - wfw[GMPE_WF_ENT_Y];
+        Real tube_length = norm2(tdx, tdy);
+        if (ph == 2 && ph > pp_eff + 1) rew -= goal * Real(3);  // july:1149
+        Real ex = s.x - wfw[GMPE_WF_ENT_X], ey = s.y - wfw[GMPE_WF_ENT_Y];
+        Real proj = ex * (tdx / tube_length) + ey * (tdy / tube_length);
+        Real edist = norm2(ex - proj * tdx, ey - proj * tdy);  // un-normalised direction, july:1154
+        if (ph == pp_eff + 1 && phase_reached == ph - 1) {     // july:1156-1160
+          if (ph == 1 && Real(0) <= proj && proj < Real(0.1) * tube_length && edist < Real(0.2) * tube_length) rew += goal * Real(3);
+          else if (ph == 2) rew += goal * Real(3);
+        }
+        if (ph == 0) {
+          rew -= norm2(wfw[GMPE_WF_ENT_X] - s.x, wfw[GMPE_WF_ENT_Y] - s.y);
+        } else if (ph == 1) {  // metering terms, july:1167-1181
+          if (front >= 0) { Real diff = fdist - sep; sp_err += diff < Real(0) ? abs_(diff) : Real(0); }
+          if (back >= 0) { Real diff = bdist - sep; sp_err += diff < Real(0) ? abs_(diff) : Real(0); }
+          if (sp_err > Real(0)) cnt[GMPE_AC_SPACING_VIOL] += 1;
+          rew -= sp_err * Real(c.formation_rew);
+          rew -= norm2(wfw[GMPE_WF_EXIT_X] - s.x, wfw[GMPE_WF_EXIT_Y] - s.y);
+          cnt[GMPE_AC_STEPS_IN_CORRIDOR] += 1;
+        } else if (ph == 2 && phase_reached == 0) {
+          cur = 0;
+        } else {  // july:1185-1194
+          if (d_goal < Real(c.goal_dist_thresh)) { if (reach) rew += goal * Real(5); }
+          else rew -= d_goal;
+        }
+        if (phase_reached == 1 && cur == 0) cnt[GMPE_AC_CONFORMANCE] += 1;
+        if (cur > phase_reached) phase_reached = cur;
+        if (cur < pp_eff) rew -= coll * Real(3);
+        if (cur < phase_reached) rew -= coll;
+        pp = cur;
+        rew = clip(rew, -Real(4) * coll, goal * Real(5));
+        rew = clip(rew, Real(c.min_reward), Real(c.max_reward));
+      } else {
+        rew -= Real(ncoll_rew) * coll;
+        if (obst) rew -= coll;
+        if (d_goal < Real(c.goal_dist_thresh)) rew += goal; else rew -= d_goal;
+      }
+      done = (st_post || sm.wstep[lw] >= c.episode_length) ? 1 : 0;  // environment.py:264-271
+      sm.done[tid] = (uint8_t)done;
+      sm.rew[tid] = rew;
+      sm.sperr[tid] = sp_err;
+      // observation uses the PRE-reward velocity and the observation-time phase
+      if (july) july_obs<Real>(pos_w, wfw, N, i, vpre.x, vpre.y, ph, sm.obs + (size_t)tid * F);
+      else {
+        Real* o = sm.obs + (size_t)tid * F;
+        V2 g = pos_w[N + i];
+        o[0] = vpre.x; o[1] = vpre.y; o[2] = s.x; o[3] = s.y; o[4] = g.x - s.x; o[5] = g.y - s.y;
+      }
+      if (do_info) {  // info_callback own-state part (july:741-787); int32 truncation as the int64 numpy arrays
+        int nearest = 0;
+        Real dmin = Real(0);
+        for (int l = 0; l < L; ++l) {
+          V2 q = pos_w[N + l];
+          Real d = norm2(s.x - q.x, s.y - q.y);
+          if (l == 0 || d < dmin) { dmin = d; nearest = l; }
+        }
+        int gr = goal_reached - 1;
+        const Real thr = Real(c.goal_dist_thresh);
+        const int32_t tnow = (int32_t)((double)sm.wstep[lw] * c.dt);
+        const int32_t pd = (int32_t)aux.x, dl = (int32_t)dmin;
+        if (dmin < thr && (nearest != gr && gr != -1)) { gr = nearest; cnt[GMPE_AC_DIST_LEFT_I] = dl; }
+        if (dmin < thr && cnt[GMPE_AC_TIME_REQ_I] == -1) { cnt[GMPE_AC_TIME_REQ_I] = tnow; cnt[GMPE_AC_DIST_TRAV_I] = pd; cnt[GMPE_AC_DIST_LEFT_I] = dl; gr = nearest; }
+        if (cnt[GMPE_AC_TIME_REQ_I] == -1) { cnt[GMPE_AC_DIST_TRAV_I] = pd; cnt[GMPE_AC_DIST_LEFT_I] = dl; }
+        if (dmin > thr && cnt[GMPE_AC_TIME_REQ_I] != -1) { cnt[GMPE_AC_DIST_TRAV_I] = pd; cnt[GMPE_AC_TIME_REQ_I] = tnow; cnt[GMPE_AC_DIST_LEFT_I] = dl; }
+        if (dmin < thr && nearest == gr) { cnt[GMPE_AC_DIST_LEFT_I] = dl; gr = nearest; }
+        goal_reached = gr + 1;
+        if (obst) cnt[GMPE_AC_OBST_COLL] += 1;
+        cnt[GMPE_AC_AGENT_COLL] += ncoll_info;
+        sm.cnew[tid * 3 + 0] = cnt[GMPE_AC_DIST_TRAV_I];
+        sm.cnew[tid * 3 + 1] = cnt[GMPE_AC_TIME_REQ_I];
+        sm.cnew[tid * 3 + 2] = cnt[GMPE_AC_SPACING_VIOL];
+      }
+    }
+    __syncthreads();
+
+    if (p.mode == MODE_STEP && active) {
+      // ---- reward / done / info outputs, state write-back ------------------------------
+      Real r_out = rew;
+      if (c.flags & GMPE_FLAG_COLLABORATIVE) {  // environment.py:1056-1059
+        Real sum = Real(0);
+        for (int k = 0; k < N; ++k) sum += sm.rew[lw * N + k];
+        r_out = sum;
+      }
+      ((Real*)p.out.reward)[ga] = r_out;
+      p.out.done[ga] = (uint8_t)done;
+      bool all_done = true;
+      for (int k = 0; k < N; ++k) all_done = all_done && sm.done[lw * N + k];
+      if (do_info) {
+        // world-level statistics are recomputed inside every agent's info_callback while
+        // later agents still hold last step's values (july:789-793, 800-823)
+        Real dm = Real(0), tm = Real(0), sv = Real(0), dsum = wfw[GMPE_WF_DELTA_SPACING];
+        for (int k = 0; k < N; ++k) {
+          const int32_t* cc = (k <= (int)i ? sm.cnew : sm.cold) + (lw * N + k) * 3;
+          dm += Real(cc[0]); tm += Real(cc[1]); sv += Real(cc[2]);
+          if (k <= (int)i) dsum += sm.sperr[lw * N + k];
+        }
+        dm /= Real(N); tm /= Real(N);
+        Real ds = Real(0), ts = Real(0);
+        for (int k = 0; k < N; ++k) {
+          const int32_t* cc = (k <= (int)i ? sm.cnew : sm.cold) + (lw * N + k) * 3;
+          Real x = Real(cc[0]) - dm, y = Real(cc[1]) - tm;
+          ds += x * x; ts += y * y;
+        }
+        ds = sqrt_(ds / Real(N)); ts = sqrt_(ts / Real(N));
+        if (p.out.info) {
+          Real* info = (Real*)p.out.info + ga * GMPE_INFO_K;
+          V4* i4 = (V4*)info;
+          i4[0] = RT<Real>::mk4(Real(cnt[GMPE_AC_DIST_LEFT_I]), Real(cnt[GMPE_AC_TIME_REQ_I]), Real(cnt[GMPE_AC_AGENT_COLL]), Real(cnt[GMPE_AC_OBST_COLL]));
+          i4[1] = RT<Real>::mk4(dm, ds, dm / (ds + Real(0.0001)), Real(cnt[GMPE_AC_DIST_TRAV_I]));
+          i4[2] = RT<Real>::mk4(Real(cnt[GMPE_AC_TIME_REQ_I]), tm, ts, tm / (ts + Real(0.0001)));
+          i4[3] = RT<Real>::mk4(Real(cnt[GMPE_AC_CONFORMANCE]) / Real(c.episode_length),
+                                dsum / (sv != Real(0) ? sv : Real(1)),
+                                Real(cnt[GMPE_AC_SPACING_VIOL]) / (cnt[GMPE_AC_STEPS_IN_CORRIDOR] != 0 ? Real(cnt[GMPE_AC_STEPS_IN_CORRIDOR]) : Real(1)),
+                                aux.y);
+        }
+        if (i == (uint32_t)(N - 1)) g_wf[(size_t)b * GMPE_WORLD_F + GMPE_WF_DELTA_SPACING] = dsum;
+        int4* gc = (int4*)(g_cnt + ga * GMPE_AGENT_CNT);
+        gc[0] = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
+        gc[1] = make_int4(cnt[4], cnt[5], cnt[6], cnt[7]);
+      }
+      const bool will_reset = (c.flags & GMPE_FLAG_AUTO_RESET) && all_done;
+      if (!will_reset) {
+        ((V4*)g_as)[ga] = s;
+        ((V2*)g_aux)[ga] = aux;
+        g_fl[ga] = (uint32_t)st_post | ((uint32_t)pp << 8) | ((uint32_t)phase_reached << 16) | ((uint32_t)goal_reached << 24);
+        if (i == 0) g_wi[(size_t)b * GMPE_WORLD_I + GMPE_WI_STEP] = sm.wstep[lw];
+      } else if (i == 0) {
+        sm.wreset[lw] = 1;
+      }
+    }
+    __syncthreads();
+
+    // ---------------- reset (auto-reset of finished worlds, or MODE_RESET) ------------------
+    // reset_world (july:339-420): counters cleared, previous_phase survives
+    const bool rs = active && sm.wreset[lw];
+    if (rs && i == 0) {
+      if (p.has_rst) {
+        const Real* rwf = (const Real*)p.rst.world_f + (size_t)b * GMPE_WORLD_F;
+        Real* wf = sm.wf + lw * GMPE_WORLD_F;
+        for (int q = 0; q < 12; ++q) wf[q] = rwf[q];
+        for (int l = 0; l < L; ++l) pos_w[N + l] = ((const V2*)p.rst.landmarks)[(size_t)b * L + l];
+        for (int o = 0; o < O; ++o) pos_w[N + L + o] = ((const V2*)p.rst.obstacles)[(size_t)b * O + o];
+        for (int q = 0; q < W; ++q) {
+          const Real* src = (const Real*)p.rst.walls + ((size_t)b * W + q) * GMPE_WALL_F;
+          Real* dst = sm.wl + (lw * W + q) * GMPE_WALL_F;
+          for (int z = 0; z < GMPE_WALL_F; ++z) dst[z] = src[z];
+          Real mid = Real(0.5) * (dst[2] + dst[3]);
+          pos_w[N + L + O + q] = dst[0] == Real(0) ? RT<Real>::mk2(mid, dst[1]) : RT<Real>::mk2(dst[1], mid);
+        }
+      } else {
+        place_world<Real>(p, sm, lw, b);
+      }
+      // persist the world-level arrays
+      Real* wf = sm.wf + lw * GMPE_WORLD_F;
+      wf[GMPE_WF_DELTA_SPACING] = Real(0);
+      for (int q = 0; q < GMPE_WORLD_F; ++q) g_wf[(size_t)b * GMPE_WORLD_F + q] = wf[q];
+      for (int l = 0; l < L; ++l) ((V2*)g_lm)[(size_t)b * L + l] = pos_w[N + l];
+      for (int o = 0; o < O; ++o) ((V2*)g_ob)[(size_t)b * O + o] = pos_w[N + L + o];
+      for (int q = 0; q < W * GMPE_WALL_F; ++q) g_wl[(size_t)b * W * GMPE_WALL_F + q] = sm.wl[lw * W * GMPE_WALL_F + q];
+      g_wi[(size_t)b * GMPE_WORLD_I + GMPE_WI_STEP] = 0;
+      g_wi[(size_t)b * GMPE_WORLD_I + GMPE_WI_EPISODE] = sm.wep[lw] + 1;
+    }
+    __syncthreads();
+    if (rs) {
+      if (p.has_rst) {
+        s = ((const V4*)p.rst.agent_state)[ga];
+        aux.y = ((const V2*)p.rst.agent_aux)[ga].y;
+      } else {
+        s = sm.nst[tid];
+        V2 g = pos_w[N + i];
+        aux.y = c.max_speed > 0 ? norm2(s.x - g.x, s.y - g.y) / Real(c.max_speed) : Real(INFINITY);  // min_time july:941-951
+      }
+      aux.x = Real(0);
+      st_post = 0; phase_reached = 0; goal_reached = 0;
+      if (heading) { Real sn, cs; sincos_(s.z, &sn, &cs); vpre = RT<Real>::mk2(s.w * cs, s.w * sn); }
+      else vpre = RT<Real>::mk2(s.z, s.w);
+      pos_w[i] = RT<Real>::mk2(s.x, s.y);
+      sm.velpre[tid] = vpre;
+      sm.velpost[tid] = vpre;
+      sm.stpost[tid] = 0;
+    }
+    __syncthreads();
+    if (rs) {
+      // observations of the fresh episode replace the terminal ones (env_wrappers.py:867-873)
+      int ph0 = 0;
+      if (july) {
+        ph0 = tube_phase<Real>(wfw, s.x, s.y, pp);
+        july_obs<Real>(pos_w, wfw, N, i, vpre.x, vpre.y, ph0, sm.obs + (size_t)tid * F);
+      } else {
+        Real* o = sm.obs + (size_t)tid * F;
+        V2 g = pos_w[N + i];
+        o[0] = vpre.x; o[1] = vpre.y; o[2] = s.x; o[3] = s.y; o[4] = g.x - s.x; o[5] = g.y - s.y;
+      }
+      ((V4*)g_as)[ga] = s;
+      ((V2*)g_aux)[ga] = aux;
+      g_fl[ga] = (uint32_t)0 | ((uint32_t)pp << 8);
+      if (do_info || p.mode == MODE_RESET) {
+        int4* gc = (int4*)(g_cnt + ga * GMPE_AGENT_CNT);
+        gc[0] = make_int4(0, 0, 0, 0);
+        gc[1] = make_int4(0, -1, -1, -1);
+      }
+    }
+    __syncthreads();
+
+    // ---------------- phase B: element-parallel output generation -------------------------
+    // obs: staged rows -> contiguous 128-bit stores
+    if (p.out.obs) {
+      Real* g_obs = (Real*)p.out.obs + (size_t)w0 * N * F;
+      const int total = nw * N * F;
+      if (p.mode == MODE_STEP) {
+        constexpr int VW = 16 / sizeof(Real);
+        const int nv = total / VW;
+        using VV = typename std::conditional<sizeof(Real) == 4, float4, double2>::type;
+        const VV* src = (const VV*)sm.obs;
+        VV* dst = (VV*)g_obs;
+        for (int q = tid; q < nv; q += nthr) dst[q] = src[q];
+        for (int q = nv * VW + tid; q < total; q += nthr) g_obs[q] = sm.obs[q];
+      } else {
+        for (int q = tid; q < total; q += nthr) {
+          uint32_t row = p.dF.div(q);
+          uint32_t w = p.dN.div(row);
+          if (sm.wwrite[w]) g_obs[q] = sm.obs[q];
+        }
+      }
+    }
+    // node_obs: [lw][j][k][8] as two 4-vectors per (ego j, entity k)  (july:1694-1771)
+    if (p.out.node_obs) {
+      Real* g_node = (Real*)p.out.node_obs + (size_t)w0 * N * E * 8;
+      const int total = nw * N * E * 2;
+      for (int q = tid; q < total; q += nthr) {
+        uint32_t half = q & 1, t = q >> 1, k, t2, j, w;
+        p.dE.divmod(t, t2, k);
+        p.dN.divmod(t2, w, j);
+        if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
+        const V2* pw = sm.pos + w * E;
+        V2 pe = pw[j], pk = pw[k];
+        V4 v;
+        if (half == 0) {
+          V2 ve = sm.velpost[w * N + j];
+          V2 vk = RT<Real>::mk2(0, 0);
+          if (k < (uint32_t)N) vk = (k <= j ? sm.velpost : sm.velpre)[w * N + k];
+          v = RT<Real>::mk4(vk.x - ve.x, vk.y - ve.y, pk.x - pe.x, pk.y - pe.y);
+        } else {
+          if (k < (uint32_t)N) {
+            V2 gk = pw[N + k];  // landmark_poses[entity.id] (july:1740)
+            v = RT<Real>::mk4(gk.x - pe.x, gk.y - pe.y, Real(0), Real(0));
+          } else {
+            Real ty = k < (uint32_t)(N + L) ? Real(1) : (k < (uint32_t)(N + L + O) ? Real(2) : Real(3));
+            v = RT<Real>::mk4(pk.x - pe.x, pk.y - pe.y, Real(1), ty);
+          }
+        }
+        ((V4*)g_node)[q] = v;
+      }
+    }
+    // adj: masked distance matrix, one copy per world (july:1625-1648)
+    if (p.out.adj) {
+      Real* g_adj = (Real*)p.out.adj + (size_t)w0 * E * E;
+      const int total = nw * E * E;
+      for (int q = tid; q < total; q += nthr) {
+        uint32_t w, rc, r, cc;
+        p.dEE.divmod(q, w, rc);
+        p.dE.divmod(rc, r, cc);
+        if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
+        const V2* pw = sm.pos + w * E;
+        const uint8_t* stw = sm.stpost + w * N;
+        bool mr = r < (uint32_t)N ? stw[r] : (r < (uint32_t)(2 * N) && r < (uint32_t)(N + L) ? stw[r - N] : 0);
+        bool mc = cc < (uint32_t)N ? stw[cc] : (cc < (uint32_t)(2 * N) && cc < (uint32_t)(N + L) ? stw[cc - N] : 0);
+        V2 a = pw[r], bb = pw[cc];
+        Real d = (r == cc || mr || mc) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
+        g_adj[q] = d;
+      }
+    }
+    // edges: warp-per-world stream compaction (ballot + popc) into the padded buffers
+    const bool env_e = (c.flags & GMPE_FLAG_ENV_EDGES) && p.out.edge_index;
+    const bool gnn_e = (c.flags & GMPE_FLAG_GNN_EDGES) && p.out.gnn_edge_index;
+    if (env_e || gnn_e) {
+      const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+      const int cap = E * (E - 1), EE = E * E;
+      const Real thr_env = Real(c.coordination_range);
+      const float thr_gnn = (float)c.gnn_max_edge_dist;
+      for (int w = warp; w < nw; w += nwarps) {
+        if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
+        const V2* pw = sm.pos + w * E;
+        const uint8_t* stw = sm.stpost + w * N;
+        const size_t gb = (size_t)(w0 + w);
+        int32_t* ei = env_e ? p.out.edge_index + gb * 2 * cap : nullptr;
+        Real* ea = env_e ? (Real*)p.out.edge_attr + gb * cap : nullptr;
+        int32_t* gi = gnn_e ? p.out.gnn_edge_index + gb * 2 * cap : nullptr;
+        Real* gea = gnn_e ? (Real*)p.out.gnn_edge_attr + gb * cap : nullptr;
+        int n_env = 0, n_gnn = 0;
+        for (int base = 0; base < EE; base += 32) {
+          int q = base + lane;
+          uint32_t r = 0, cc = 0;
+          Real d = Real(0);
+          if (q < EE) {
+            p.dE.divmod(q, r, cc);
+            bool mr = r < (uint32_t)N ? stw[r] : (r < (uint32_t)(2 * N) && r < (uint32_t)(N + L) ? stw[r - N] : 0);
+            bool mc = cc < (uint32_t)N ? stw[cc] : (cc < (uint32_t)(2 * N) && cc < (uint32_t)(N + L) ? stw[cc - N] : 0);
+            V2 a = pw[r], bb = pw[cc];
+            d = (r == cc || mr || mc) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
+          }
+          if (env_e) {  // update_graph: (d <= max_edge_dist) & (d > 0), row-major (july:1660-1665)
+            bool on = d > Real(0) && d <= thr_env;
+            unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) {
+              int slot = n_env + __popc(m & ((1u << lane) - 1));
+              ei[slot] = (int32_t)r; ei[cap + slot] = (int32_t)cc; ea[slot] = d;
+            }
+            n_env += __popc(m);
+          }
+          if (gnn_e) {  // process_adj on the fp32 cast: (adj < max_edge_dist) & (adj > 0) (gnn_new.py:339)
+            float df = (float)d;
+            bool on = df > 0.0f && df < thr_gnn;
+            unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) {
+              int slot = n_gnn + __popc(m & ((1u << lane) - 1));
+              gi[slot] = (int32_t)r; gi[cap + slot] = (int32_t)cc; gea[slot] = Real(df);
+            }
+            n_gnn += __popc(m);
+          }
+        }
+        if (env_e) {
+          for (int q = n_env + lane; q < cap; q += 32) { ei[q] = -1; ei[cap + q] = -1; ea[q] = Real(0); }
+          if (lane == 0) p.out.num_edges[gb] = n_env;
+        }
+        if (gnn_e) {
+          for (int q = n_gnn + lane; q < cap; q += 32) { gi[q] = -1; gi[cap + q] = -1; gea[q] = Real(0); }
+          if (lane == 0) p.out.gnn_num_edges[gb] = n_gnn;
+        }
+      }
+    }
+    __syncthreads();  // smem is reused by the next tile
+  }
+}
+
+// argmax over the one-hot action rows the runner builds (graph_mpe_runner.py:375-377;
+// environment.py:431, 444): first maximum wins, like np.argmax.
+template <typename T>
+__global__ void decode_onehot_kernel(const T* __restrict__ onehot, int32_t* __restrict__ idx, int64_t rows, int A) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const T* row = onehot + r * A;
+  int best = 0;
+  T bv = row[0];
+  for (int a = 1; a < A; ++a) { T v = row[a]; if (v > bv) { bv = v; best = a; } }
+  idx[r] = best;
+}
+
+}  // namespace gmpe

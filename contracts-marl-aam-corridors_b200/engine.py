@@ -1,0 +1,158 @@
+"""BatchedGraphMPE -- one GPU-resident batch of B independent GraphMPE worlds.
+
+Owns the device tensors (state + per-step outputs, all caller-owned as far as the C ABI
+is concerned) and drives the CUDA library through ``include/gmpe.h``.  torch is used for
+device memory and streams only; every number is produced by the hand-written kernels in
+``csrc/``.  There is no CPU fallback: constructing an engine without the built library or
+without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi, buffers
+
+
+class BatchedGraphMPE:
+    def __init__(self, cfg: abi.GmpeConfig, device: int | str | torch.device = 0):
+        if not torch.cuda.is_available():
+            raise abi.GmpeError("BatchedGraphMPE needs a CUDA device (no CPU fallback for the step path)")
+        self.lib = abi.load_library()
+        self.cfg = cfg.copy()
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if self.device.type != "cuda":
+            raise abi.GmpeError("device must be a CUDA device")
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device(f"cuda:{dev_index}")
+        self.real = torch.float64 if cfg.precision == abi.F64 else torch.float32
+        self.B, self.N = cfg.num_worlds, cfg.num_agents
+        self.layout = abi.layout_for(cfg)
+        self.E = self.layout.num_entities
+        h = C.c_void_p()
+        rc = self.lib.gmpe_create(C.byref(self.cfg), dev_index, C.byref(h))
+        if rc != abi.OK:
+            raise abi.GmpeError(f"gmpe_create failed ({rc}): {self.lib.gmpe_last_error(None).decode()}")
+        self._h = h
+        kinds = {"real": self.real, "i32": torch.int32, "u8": torch.uint8}
+        sh = buffers.shapes(cfg)
+        with torch.cuda.device(self.device):
+            self.state = {n: torch.zeros(sh[n][0], dtype=kinds[sh[n][1]], device=self.device) for n in buffers.STATE_FIELDS}
+            self.state["agent_cnt"][..., abi.AC_TIME_REQ_I:] = -1
+            self.out = {n: torch.zeros(sh[n][0], dtype=kinds[sh[n][1]], device=self.device)
+                        for n in buffers.wanted_outputs(cfg)}
+            self.action_idx = torch.zeros((self.B, self.N), dtype=torch.int32, device=self.device)
+        self._st = buffers.make_struct(abi.GmpeState, self.state)
+        self._out = buffers.make_struct(abi.GmpeStepOut, self.out)
+        self._null_inject = abi.GmpeStepInject()
+
+    # -- plumbing -------------------------------------------------------------------
+    def _check(self, rc: int, what: str) -> None:
+        if rc != abi.OK:
+            raise abi.GmpeError(f"{what} failed ({rc}): {self.lib.gmpe_last_error(self._h).decode()}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.gmpe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.gmpe_launch_count(self._h))
+
+    def _inject(self, theta_draw, reset_state):
+        if theta_draw is None and reset_state is None:
+            return self._null_inject, None
+        if theta_draw is not None:
+            theta_draw = torch.as_tensor(theta_draw, dtype=self.real, device=self.device).contiguous()
+        if reset_state is not None:
+            rs = {}
+            for k, v in reset_state.items():
+                t = torch.as_tensor(v, device=self.device)
+                rs[k] = t.to(self.real if t.is_floating_point() else t.dtype).contiguous()
+            reset_state = rs
+        return buffers.make_inject(theta_draw, reset_state)
+
+    # -- hot path ---------------------------------------------------------------------
+    def reset(self, env_mask=None, reset_state: dict | None = None) -> dict:
+        """MultiAgentGraphEnv.reset for every masked world (environment.py:1066-1081)."""
+        inj, keep = self._inject(None, reset_state)
+        m = None
+        if env_mask is not None:
+            m = torch.as_tensor(env_mask, device=self.device).to(torch.uint8).contiguous()
+        rc = self.lib.gmpe_reset(self._h, C.byref(self._st), m.data_ptr() if m is not None else None,
+                                 C.byref(inj), C.byref(self._out), self._stream())
+        self._check(rc, "gmpe_reset")
+        self._keep = (keep, m)
+        return self.out
+
+    def step(self, action_idx: torch.Tensor, theta_draw=None, reset_state: dict | None = None) -> dict:
+        """One env step for the whole batch. ``action_idx``: int32 (B, N) device tensor."""
+        if action_idx.dtype != torch.int32 or action_idx.device != self.device or not action_idx.is_contiguous():
+            action_idx = action_idx.to(device=self.device, dtype=torch.int32).contiguous()
+        if tuple(action_idx.shape) != (self.B, self.N):
+            raise ValueError(f"action_idx must have shape {(self.B, self.N)}, got {tuple(action_idx.shape)}")
+        inj, keep = self._inject(theta_draw, reset_state)
+        rc = self.lib.gmpe_step(self._h, C.byref(self._st), action_idx.data_ptr(), C.byref(inj),
+                                C.byref(self._out), self._stream())
+        self._check(rc, "gmpe_step")
+        self._keep = (keep, action_idx)
+        return self.out
+
+    def decode_onehot(self, onehot: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """argmax of the runner's one-hot actions (environment.py:431,444) on device."""
+        A = self.cfg.total_actions
+        if tuple(onehot.shape) != (self.B, self.N, A):
+            raise ValueError(f"one-hot actions must have shape {(self.B, self.N, A)}, got {tuple(onehot.shape)}")
+        if onehot.dtype not in (torch.float32, torch.float64):
+            onehot = onehot.to(torch.float32)
+        onehot = onehot.to(self.device).contiguous()
+        out = self.action_idx if out is None else out
+        rc = self.lib.gmpe_decode_onehot(self._h, onehot.data_ptr(), onehot.element_size(), out.data_ptr(), self._stream())
+        self._check(rc, "gmpe_decode_onehot")
+        self._keep = (onehot,)
+        return out
+
+    # -- checkpoint / teacher forcing ---------------------------------
+    def state_dict(self) -> dict:
+        return {k: v.clone() for k, v in self.state.items()}
+
+    def load_state_dict(self, sd: dict) -> None:
+        for k, v in sd.items():
+            t = torch.as_tensor(v, device=self.device)
+            self.state[k].copy_(t.to(self.state[k].dtype).reshape(self.state[k].shape))
+
+    # -- roofline bookkeeping -------------------------------------------------------------
+    def algorithmic_bytes_per_env_step(self) -> int:
+        """Bytes one env-step must move if every logical array is touched exactly once
+        (after SURVEY.md section 8d, extended by the info arrays this build keeps)."""
+        c = self.cfg
+        R = self.layout.real_bytes
+        N, L, O, W, E = c.num_agents, c.num_landmarks, c.num_obstacles, c.num_walls, self.E
+        F, cap = self.layout.obs_dim, self.layout.edge_cap
+        b = 2 * (4 * R * N)            # agent_state r+w
+        b += 2 * (2 * R * N)           # agent_aux r+w
+        b += 2 * (4 * N)               # agent_flags r+w
+        b += 4 * N                     # action index in
+        b += R * N + N                 # reward + done out
+        b += R * abi.WORLD_F + 2 * 4   # world frame in, step counter r+w
+        b += 2 * R * (L + O) + abi.WALL_F * R * W
+        b += R * F * N + R * 8 * N * E + R * E * E
+        if c.flags & abi.FLAG_INFO:
+            b += 2 * (4 * abi.AGENT_CNT * N) + R * abi.INFO_K * N
+        if c.flags & abi.FLAG_ENV_EDGES:
+            b += (8 + R) * cap + 4
+        if c.flags & abi.FLAG_GNN_EDGES:
+            b += (8 + R) * cap + 4
+        return int(b)
