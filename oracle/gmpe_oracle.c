@@ -510,7 +510,9 @@ static double july_reward(World* w, int i, double theta_draw) {
   if (is_obstacle_collision(w, s, c->entity_size)) rew -= c->collision_rew * 3;
   double tdx = w->wf[GMPE_WF_EXIT_X] - w->wf[GMPE_WF_ENT_X], tdy = w->wf[GMPE_WF_EXIT_Y] - w->wf[GMPE_WF_ENT_Y];
   double tube_length = norm2(tdx, tdy);
-  double hx = cos(s[2]), hy = sin(s[2]);
+  /* agent.state.theta: the heading state, or arctan2(vy, vx) for the double integrator (core:188-189) */
+  double theta = is_kin_heading(c) ? s[2] : atan2(s[3], s[2]);
+  double hx = cos(theta), hy = sin(theta);
   int front = -1, back = -1;
   double fproj = 0, bproj = 0;
   for (int k = 0; k < w->N; ++k) { /* july:1136-1143 */
