@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the GraphMPE step path (env step + graph obs).
+
+    python bench.py --gpus N --steps K --warmup W            # this build (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, all host cores)
+
+For N > 1 the driver launches it under torchrun (one rank per GPU, NCCL).  One JSON line is
+printed by rank 0.  Workload = BASELINE.json configs[1]: navigation_graph, 3 agents / 3
+landmarks, 65,536 worlds per GPU (weak scaling: the worlds of a rank are independent, there
+is no per-step collective; one NCCL all-reduce of the episode statistics per rollout).
+
+A "step" is one pass of the hot path over the batch: fused kernel = _set_action + World.step
++ observation / reward / graph_observation / done / info for every agent of every world,
+including auto-reset.  `value` times it with inputs resident in HBM (CUDA events around each
+step on the launching stream, L2 flushed before every timed step); `e2e` times the same
+metric through the reference-facing GraphSubprocVecEnv.step with HOST buffers (the one-hot
+float64 action block the runner builds going in, every returned tensor coming back to pinned
+host memory), copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1] (the configuration the metric is quoted on)
+    "navigation_graph_n3_b65536": dict(
+        args=dict(scenario_name="navigation_graph", dynamics_type="double_integrator", num_agents=3,
+                  num_landmarks=3, num_obstacles=0, num_walls=0, world_size=2, episode_length=25,
+                  total_actions=5, collaborative=True, use_dones=False, goal_rew=5, collision_rew=5, max_speed=2),
+        worlds_per_gpu=65536),
+    # BASELINE.json configs[2]
+    "july_air_taxi_n3_b131072": dict(
+        args=dict(scenario_name="nav_metered_one_goal_graph_rotate_tube_july", dynamics_type="air_taxi",
+                  num_agents=3, num_landmarks=3, world_size=3, episode_length=200, goal_rew=30, collision_rew=5,
+                  formation_rew=1, collaborative=False, use_dones=False, max_speed=2),
+        worlds_per_gpu=131072),
+    # BASELINE.json configs[3]
+    "navigation_graph_n16_o8_w4": dict(
+        args=dict(scenario_name="navigation_graph", dynamics_type="double_integrator", num_agents=16,
+                  num_landmarks=16, num_obstacles=8, num_walls=4, world_size=4, episode_length=25,
+                  total_actions=5, collaborative=True, max_speed=2),
+        worlds_per_gpu=16384),
+    # BASELINE.json configs[4]
+    "july_air_taxi_n64": dict(
+        args=dict(scenario_name="nav_metered_one_goal_graph_rotate_tube_july", dynamics_type="air_taxi",
+                  num_agents=64, num_landmarks=64, world_size=12, episode_length=200, goal_rew=30,
+                  collision_rew=5, formation_rew=1, collaborative=False, max_speed=2),
+        worlds_per_gpu=4096),
+}
+DEFAULT_WORKLOAD = "navigation_graph_n3_b65536"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.samples, self._stop, self._t = gpu_index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(s[2 + j].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_leg(cfg_args, worlds, steps, warmup, nthreads, max_seconds=25.0):
+    """Time the oracle port (oracle/gmpe_oracle.c: fp64, RK45 where the reference uses it)
+    on the host cores.  Returns (agent_steps_per_s, steps_done, ms_per_step)."""
+    from gmpe_b200 import default_args, make_config
+    from oracle.oracle import OracleEnv
+
+    args = default_args(**cfg_args)
+    cfg = make_config(args, worlds, precision="fp64", seed=1, env_edges=True, info=True)
+    env = OracleEnv(cfg, use_rk45=True, nthreads=nthreads)
+    env.reset()
+    rs = np.random.RandomState(0)
+    acts = rs.randint(cfg.total_actions, size=(8, worlds, cfg.num_agents)).astype(np.int32)
+    for t in range(warmup):
+        env.step(acts[t % 8])
+    t0 = time.perf_counter()
+    done = 0
+    for t in range(steps):
+        env.step(acts[t % 8])
+        done += 1
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return worlds * cfg.num_agents * done / dt, done, dt / done * 1e3
+
+
+def run_reference(opts):
+    """--impl reference: the reference's own algorithm for this path on the box's host cores.
+    The reference is pure Python and cannot travel to the GPU box, so this arm runs the C
+    port of it (oracle/, pinned to the reference's golden traces) with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[opts.workload]
+    worlds = opts.worlds or wl["worlds_per_gpu"]
+    cores = os.cpu_count() or 1
+    value, done, ms = cpu_leg(wl["args"], worlds, opts.steps, max(opts.warmup, 1), cores, max_seconds=120.0)
+    N = wl["args"]["num_agents"]
+    line = {
+        "impl": "reference", "metric": "agent-steps/sec (env step + graph obs)", "value": value,
+        "unit": "agent-steps/s", "n_gpus": opts.gpus, "steps": done, "warmup": opts.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": opts.workload, "worlds": worlds, "num_agents": N,
+                   "scenario": wl["args"]["scenario_name"], "episode_length": wl["args"]["episode_length"]},
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{done} steps of the full {worlds}-world batch, {cores} pthreads, C port of the "
+                                   "reference step (oracle/gmpe_oracle.c)"},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(opts):
+    import torch
+
+    from gmpe_b200 import default_args, dist as gdist, make_config
+    from gmpe_b200.engine import BatchedGraphMPE
+    from gmpe_b200.env_wrappers import GraphSubprocVecEnv
+
+    rank, local, world = gdist.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    wl = WORKLOADS[opts.workload]
+    args = default_args(**wl["args"])
+    Bg = opts.worlds or wl["worlds_per_gpu"]
+    N = args.num_agents
+    offset = rank * Bg  # weak scaling: fixed worlds per GPU, world ids are global
+    cfg = make_config(args, Bg, precision="fp32", seed=1, world_offset=offset, auto_reset=True,
+                      env_edges=True, gnn_edges=False, info=True)
+    eng = BatchedGraphMPE(cfg, dev)
+    K, W = opts.steps, max(opts.warmup, 3)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    acts = torch.randint(0, cfg.total_actions, (K + W, Bg, N), generator=gen, device=dev, dtype=torch.int32)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    eng.reset()
+    for t in range(W):
+        eng.step(acts[t])
+    torch.cuda.synchronize()
+    launches0 = eng.launch_count
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stream = torch.cuda.current_stream(dev)
+    gdist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        for t in range(K):
+            flush.zero_()  # evict the previous step's lines: every timed step starts with a cold L2
+            starts[t].record(stream)
+            eng.step(acts[W + t])
+            stops[t].record(stream)
+        launches = eng.launch_count - launches0  # kernels of this build launched inside the timed region
+        stats = eng_stats(eng, torch)
+        gdist.reduce_stats(stats)  # the once-per-rollout NCCL reduction (no per-step collective)
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+        # keep the sampler alive for at least a second of load so the clocks line is meaningful
+        t_end = time.perf_counter() + 1.0
+        tt = 0
+        while time.perf_counter() < t_end:
+            eng.step(acts[W + (tt % K)])
+            tt += 1
+        torch.cuda.synchronize()
+    gdist.barrier()
+    per_step_ms = np.array([starts[t].elapsed_time(stops[t]) for t in range(K)])
+    total_ms = gdist.max_over_ranks(float(per_step_ms.sum()), dev)
+    ms_per_step = total_ms / K
+    value = world * Bg * N * K / (total_ms * 1e-3)
+
+    # hot-L2 rollout mode (no flush, K steps back to back) -- reported, not the headline
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(K):
+        eng.step(acts[W + t])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    hot_ms = gdist.max_over_ranks(e0.elapsed_time(e1), dev) / K
+
+    # roofline of the dominant (only) kernel of the step
+    abytes = eng.algorithmic_bytes_per_env_step() * Bg
+    peak, peak_src = load_peaks()
+    kernel_ms = float(per_step_ms.mean())
+    achieved = abytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(opts.workload)
+        except Exception:
+            traffic = None
+
+    # e2e through the reference-facing vec env with host buffers
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    venv = GraphSubprocVecEnv(args=args, num_envs=Bg, device=dev, seed=1, world_offset=offset, info=True)
+    venv.reset()
+    A = cfg.total_actions
+    Ke = max(3, min(K, opts.e2e_steps))
+    rs = np.random.RandomState(5 + rank)
+    onehots = [np.eye(A)[rs.randint(A, size=(Bg, N))] for _ in range(4)]  # float64, as graph_mpe_runner.py:375-377
+    for t in range(3):
+        venv.step(onehots[t % 4], 0)
+    gdist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sink = 0.0
+    for t in range(Ke):
+        o = venv.step(onehots[t % 4], 0)
+        sink += float(o[4][0, 0])  # touch the host result
+    torch.cuda.synchronize()
+    e2e_s = gdist.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = world * Bg * N * Ke / e2e_s
+    h2d, d2h = venv.h2d_bytes_last, venv.d2h_bytes_last
+    venv.close()
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not opts.no_cpu:
+        cores = os.cpu_count() or 1
+        sample_worlds = min(Bg, 16384)
+        v, done, ms = cpu_leg(wl["args"], sample_worlds, 50, 2, cores, max_seconds=15.0)
+        cpu = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+               "sample": f"{done} steps x {sample_worlds} worlds of the same workload, {cores} pthreads, "
+                         "oracle/gmpe_oracle.c (fp64 C port of the reference step)"}
+    line = {
+        "metric": "agent-steps/sec (env step + graph obs)", "value": value, "unit": "agent-steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": opts.workload, "scenario": args.scenario_name, "worlds_per_gpu": Bg,
+                   "worlds_total": Bg * world, "num_agents": N, "num_landmarks": args.num_landmarks,
+                   "num_obstacles": args.num_obstacles, "num_walls": args.num_walls,
+                   "episode_length": args.episode_length, "actions": "seeded uniform random discrete, resident in HBM",
+                   "l2": "flushed before every timed step (256 MiB memset outside the event pair); "
+                         "per-step CUDA events on the launching stream",
+                   "outputs": "obs,node_obs,adj,reward,done,info,env edges", "parallelism": f"dp{world} (sharded worlds)"},
+        "env_steps_per_s": value / N,
+        "hot_l2": {"ms_per_step": hot_ms, "value": world * Bg * N / (hot_ms * 1e-3),
+                   "note": "K steps back to back without the flush (rollout mode)"},
+        "wall_s_timed_region": t_wall,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "gmpe_step_kernel<float>",
+                     "algorithmic_bytes_per_launch": abytes, "kernel_ms": kernel_ms},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "steps": Ke,
+                "api": "GraphSubprocVecEnv.step(one-hot float64 host actions) -> host numpy views (pinned)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "rollout_stats": [float(x) for x in stats.cpu().tolist()],
+    }
+    print(json.dumps(line), flush=True)
+
+
+def eng_stats(eng, torch):
+    from gmpe_b200 import abi
+
+    cnt = eng.state["agent_cnt"].to(torch.float64)
+    return torch.stack([eng.out["reward"].to(torch.float64).sum(), cnt[..., abi.AC_AGENT_COLL].sum(),
+                        cnt[..., abi.AC_OBST_COLL].sum(), eng.out["done"].to(torch.float64).sum()])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--worlds", type=int, default=0, help="worlds per GPU (default: the workload's)")
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--no-cpu", action="store_true")
+    opts = ap.parse_args()
+    if opts.impl == "reference":
+        run_reference(opts)
+    else:
+        run_ours(opts)
+
+
+if __name__ == "__main__":
+    main()

@@ -97,7 +97,7 @@ class GmpeState(C.Structure):
 class GmpeStepOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "obs", "node_obs", "adj", "reward", "done", "info", "edge_index", "edge_attr", "num_edges",
-        "gnn_edge_index", "gnn_edge_attr", "gnn_num_edges")]
+        "gnn_edge_index", "gnn_edge_attr", "gnn_num_edges", "indiv_reward")]
 
 
 class GmpeStepInject(C.Structure):
@@ -107,7 +107,7 @@ class GmpeStepInject(C.Structure):
 #: every symbol include/gmpe.h declares
 EXPORTED_SYMBOLS = (
     "gmpe_abi_version", "gmpe_create", "gmpe_destroy", "gmpe_last_error", "gmpe_layout",
-    "gmpe_reset", "gmpe_step", "gmpe_decode_onehot", "gmpe_launch_count",
+    "gmpe_reset", "gmpe_step", "gmpe_decode_onehot", "gmpe_launch_count", "gmpe_set_seed",
 )
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -150,6 +150,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.gmpe_decode_onehot.restype = C.c_int
     lib.gmpe_launch_count.argtypes = [C.c_void_p]
     lib.gmpe_launch_count.restype = C.c_int64
+    lib.gmpe_set_seed.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
+    lib.gmpe_set_seed.restype = C.c_int
     v = lib.gmpe_abi_version()
     if v != ABI_VERSION:
         raise GmpeError(f"ABI mismatch: library reports {v}, python mirror expects {ABI_VERSION}; rebuild")

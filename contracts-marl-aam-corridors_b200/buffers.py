@@ -14,7 +14,7 @@ from . import abi
 STATE_FIELDS = ("agent_state", "agent_aux", "agent_flags", "agent_cnt", "world_f", "world_i",
                 "landmarks", "obstacles", "walls")
 OUT_FIELDS = ("obs", "node_obs", "adj", "reward", "done", "info", "edge_index", "edge_attr",
-              "num_edges", "gnn_edge_index", "gnn_edge_attr", "gnn_num_edges")
+              "num_edges", "gnn_edge_index", "gnn_edge_attr", "gnn_num_edges", "indiv_reward")
 
 
 def shapes(cfg: abi.GmpeConfig) -> dict:
@@ -44,13 +44,14 @@ def shapes(cfg: abi.GmpeConfig) -> dict:
         "gnn_edge_index": ((B, 2, cap), "i32"),
         "gnn_edge_attr": ((B, cap), "real"),
         "gnn_num_edges": ((B,), "i32"),
+        "indiv_reward": ((B, N), "real"),
     }
 
 
 def wanted_outputs(cfg: abi.GmpeConfig) -> tuple:
     names = ["obs", "node_obs", "adj", "reward", "done"]
     if cfg.flags & abi.FLAG_INFO:
-        names.append("info")
+        names += ["indiv_reward", "info"]
     if cfg.flags & abi.FLAG_ENV_EDGES:
         names += ["edge_index", "edge_attr", "num_edges"]
     if cfg.flags & abi.FLAG_GNN_EDGES:

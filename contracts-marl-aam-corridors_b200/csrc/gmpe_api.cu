@@ -157,6 +157,13 @@ const char* gmpe_last_error(gmpe_handle h) { return h ? h->err.c_str() : g_creat
 
 int64_t gmpe_launch_count(gmpe_handle h) { return h ? h->launches : 0; }
 
+int gmpe_set_seed(gmpe_handle h, uint64_t seed, int64_t world_offset) {
+  if (!h) return GMPE_E_NULL;
+  h->cfg.seed = seed;
+  h->cfg.world_offset = world_offset;
+  return GMPE_OK;
+}
+
 static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* act, const uint8_t* mask,
                   const GmpeStepInject* inj, const GmpeStepOut* out, void* stream) {
   const GmpeConfig& c = h->cfg;

@@ -672,6 +672,7 @@ __global__ void __launch_bounds__(256) gmpe_step_kernel(const __grid_constant__ 
         r_out = sum;
       }
       ((Real*)p.out.reward)[ga] = r_out;
+      if (p.out.indiv_reward) ((Real*)p.out.indiv_reward)[ga] = rew;
       p.out.done[ga] = (uint8_t)done;
       bool all_done = true;
       for (int k = 0; k < N; ++k) all_done = all_done && sm.done[lw * N + k];

@@ -41,8 +41,21 @@ class BatchedGraphMPE:
         with torch.cuda.device(self.device):
             self.state = {n: torch.zeros(sh[n][0], dtype=kinds[sh[n][1]], device=self.device) for n in buffers.STATE_FIELDS}
             self.state["agent_cnt"][..., abi.AC_TIME_REQ_I:] = -1
-            self.out = {n: torch.zeros(sh[n][0], dtype=kinds[sh[n][1]], device=self.device)
-                        for n in buffers.wanted_outputs(cfg)}
+            # All outputs are views of ONE device arena (256-byte aligned slabs) so that a host
+            # consumer can fetch everything a step returns with a single device->host copy.
+            names = buffers.wanted_outputs(cfg)
+            offs, off = {}, 0
+            for n in names:
+                nbytes = int(np.prod(sh[n][0])) * torch.empty((), dtype=kinds[sh[n][1]]).element_size()
+                offs[n] = (off, nbytes)
+                off = (off + nbytes + 255) // 256 * 256
+            self.out_arena = torch.zeros(max(off, 256), dtype=torch.uint8, device=self.device)
+            self.out_slabs = offs
+            self.out = {n: self.out_arena[o:o + nb].view(kinds[sh[n][1]]).view(sh[n][0]) for n, (o, nb) in offs.items()}
+            #: bytes from the arena start that hold what MultiAgentGraphEnv.step returns
+            #: (obs, node_obs, adj, reward, done[, indiv_reward, info]); edges come after
+            host_names = [n for n in names if n in ("obs", "node_obs", "adj", "reward", "done", "indiv_reward", "info")]
+            self.host_prefix_bytes = max(offs[n][0] + offs[n][1] for n in host_names)
             self.action_idx = torch.zeros((self.B, self.N), dtype=torch.int32, device=self.device)
         self._st = buffers.make_struct(abi.GmpeState, self.state)
         self._out = buffers.make_struct(abi.GmpeStepOut, self.out)
@@ -66,6 +79,14 @@ class BatchedGraphMPE:
             self.close()
         except Exception:
             pass
+
+    def set_seed(self, seed: int, world_offset: int | None = None) -> None:
+        """env.seed(seed) of the reference (environment.py:219-223): re-keys the Philox streams."""
+        if world_offset is None:
+            world_offset = self.cfg.world_offset
+        self.cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.cfg.world_offset = int(world_offset)
+        self._check(self.lib.gmpe_set_seed(self._h, self.cfg.seed, self.cfg.world_offset), "gmpe_set_seed")
 
     @property
     def launch_count(self) -> int:

@@ -1,0 +1,293 @@
+"""Vectorised env wrappers with the reference's interface
+(onpolicy/envs/env_wrappers.py:29-140, 851-1037), backed by ONE GPU-resident batch.
+
+``GraphSubprocVecEnv(env_fns)`` / ``GraphDummyVecEnv(env_fns)`` take the same list of env
+constructors the reference's ``make_train_env`` builds (onpolicy/scripts/train_mpe.py:21-43).
+Only ``env_fns[0]`` is called (it yields the args, spaces and seed); ``len(env_fns)`` is the
+number of worlds B.  Instead of B processes exchanging pickles over pipes, ``step`` is: one
+host->device copy of the action block, two kernel launches (one-hot argmax, fused step incl.
+auto-reset), one device->host copy of the whole output arena into pinned memory.
+
+Returned arrays follow the reference's shapes:
+  reset -> obs (B,N,F), ag_ids (B,N,1), node_obs (B,N,E,8), adj (B,N,E,E)
+  step  -> (..., rews (B,N) or (B,N,1) when collaborative, dones (B,N) bool, infos)
+           GraphDummyVecEnv appends ``reset_count`` as an 8th value.
+Differences, all documented in INTEGRATION.md: arrays are float32 (the only consumer casts to
+float32, onpolicy/utils/graph_buffer.py:84-113); they are views of a double-buffered pinned
+arena, valid until the step after next; ``adj`` is a stride-0 broadcast of the single
+per-world matrix the reference aliases N times; ``infos`` is a lazy sequence.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import abi
+from .config import make_config
+from .engine import BatchedGraphMPE
+from .environment import build_spaces
+
+
+class ShareVecEnv(ABC):  # env_wrappers.py:29-140
+    closed = False
+    viewer = None
+    metadata = {"render.modes": ["human", "rgb_array"]}
+
+    def __init__(self, num_envs, observation_space, share_observation_space, action_space):
+        self.num_envs = num_envs
+        self.observation_space = observation_space
+        self.share_observation_space = share_observation_space
+        self.action_space = action_space
+
+    @abstractmethod
+    def reset(self):
+        pass
+
+    @abstractmethod
+    def step_async(self, actions):
+        pass
+
+    @abstractmethod
+    def step_wait(self):
+        pass
+
+    def close_extras(self):
+        pass
+
+    def close(self):
+        if self.closed:
+            return
+        self.close_extras()
+        self.closed = True
+
+    def step(self, actions, num_current_episode: Optional[int] = None):
+        self.step_async(actions, num_current_episode)
+        return self.step_wait()
+
+    def render(self, mode="human"):
+        raise NotImplementedError("rendering is out of scope of this build")
+
+    @property
+    def unwrapped(self):
+        return self
+
+
+class _AgentInfo:
+    """dict-like view of one (env, agent) row of the info tensor."""
+    __slots__ = ("_row", "_rew")
+
+    def __init__(self, row, rew):
+        self._row, self._rew = row, rew
+
+    def keys(self):
+        return ("individual_reward",) + abi.INFO_KEYS
+
+    def __contains__(self, k):
+        return k in self.keys()
+
+    def __getitem__(self, k):
+        if k == "individual_reward":
+            return self._rew
+        return self._row[abi.INFO_KEYS.index(k)]
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self.keys())
+
+    def to_dict(self):
+        return dict(self.items())
+
+
+class LazyInfos:
+    """``infos[env][agent][key]`` as GMPERunner.process_infos walks it
+    (onpolicy/runner/shared/base_runner.py:194-284) without building B*N python dicts."""
+
+    def __init__(self, info: np.ndarray, indiv_reward: np.ndarray):
+        self.info, self.rew = info, indiv_reward
+
+    def __len__(self):
+        return self.info.shape[0]
+
+    def __getitem__(self, e):
+        if isinstance(e, slice):
+            return [self[i] for i in range(*e.indices(len(self)))]
+        if e < 0:
+            e += len(self)
+        return [_AgentInfo(self.info[e, a], self.rew[e, a]) for a in range(self.info.shape[1])]
+
+    def __iter__(self):
+        return (self[e] for e in range(len(self)))
+
+
+class _BatchedVecEnv(ShareVecEnv):
+    returns_reset_count = False
+
+    def __init__(self, env_fns=None, spaces=None, *, args=None, num_envs=None, device=0, precision="fp32",
+                 seed=None, world_offset=0, output="numpy", info=True, env_edges=False, gnn_edges=False):
+        if args is None:
+            if not env_fns:
+                raise ValueError("need env_fns (reference calling convention) or args=/num_envs=")
+            env0 = env_fns[0]()
+            args = env0.world.all_args
+            if seed is None:
+                seed = getattr(env0, "_seed", None)
+            env0.close()
+            num_envs = len(env_fns)
+        if seed is None:
+            seed = getattr(args, "seed", 1)
+        self.all_args = args
+        self.cfg = make_config(args, num_envs, precision=precision, seed=seed, world_offset=world_offset,
+                               auto_reset=True, env_edges=env_edges, gnn_edges=gnn_edges, info=info)
+        self.engine = BatchedGraphMPE(self.cfg, device)
+        sp = build_spaces(args, self.cfg)
+        ShareVecEnv.__init__(self, num_envs, sp["observation_space"], sp["share_observation_space"], sp["action_space"])
+        for k in ("node_observation_space", "adj_observation_space", "edge_observation_space",
+                  "agent_id_observation_space", "share_agent_id_observation_space"):
+            setattr(self, k, sp[k])
+        self.output = output
+        self.waiting = False
+        self.closed = False
+        B, N, A = num_envs, self.cfg.num_agents, self.cfg.total_actions
+        self.num_agents = N
+        self._A = A
+        self._ag_ids = np.broadcast_to(np.arange(N, dtype=np.int64).reshape(1, N, 1), (B, N, 1))
+        dev = self.engine.device
+        # pinned staging: action block in (both element widths the runner may hand over) and
+        # a double-buffered arena out
+        self._act_pin = {4: torch.empty((B, N, A), dtype=torch.float32).pin_memory(),
+                         8: torch.empty((B, N, A), dtype=torch.float64).pin_memory()}
+        self._act_dev = {4: torch.empty((B, N, A), dtype=torch.float32, device=dev),
+                         8: torch.empty((B, N, A), dtype=torch.float64, device=dev)}
+        self._idx_pin = torch.empty((B, N), dtype=torch.int32).pin_memory()
+        nbytes = self.engine.host_prefix_bytes
+        self._arena = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._flip = 0
+        self.h2d_bytes_last = 0
+        self.d2h_bytes_last = nbytes
+
+    # -- host views of the pinned arena ---------------------------------------------------
+    def _host_views(self, arena: torch.Tensor) -> dict:
+        np_arena = arena.numpy()
+        eng = self.engine
+        real = np.float64 if self.cfg.precision == abi.F64 else np.float32
+        kinds = {"obs": real, "node_obs": real, "adj": real, "reward": real, "indiv_reward": real, "info": real,
+                 "done": np.uint8}
+        out = {}
+        for n, (off, nb) in eng.out_slabs.items():
+            if n in kinds and off + nb <= np_arena.size:
+                out[n] = np_arena[off:off + nb].view(kinds[n]).reshape(tuple(eng.out[n].shape))
+        return out
+
+    def _fetch(self):
+        if self.output == "torch":
+            return dict(self.engine.out)
+        arena = self._arena[self._flip]
+        self._flip ^= 1
+        arena.copy_(self.engine.out_arena[:arena.numel()], non_blocking=True)
+        torch.cuda.current_stream(self.engine.device).synchronize()
+        return self._host_views(arena)
+
+    def _pack_obs(self, o):
+        B, N, E = self.num_envs, self.num_agents, self.engine.E
+        if self.output == "torch":
+            adj = o["adj"].unsqueeze(1).expand(B, N, E, E)
+            ids = torch.as_tensor(np.ascontiguousarray(self._ag_ids), device=self.engine.device)
+            return o["obs"], ids, o["node_obs"], adj
+        adj = np.broadcast_to(o["adj"][:, None], (B, N, E, E))
+        return o["obs"], self._ag_ids, o["node_obs"], adj
+
+    # -- reference interface ------------------------------------------------------------
+    def reset(self, num_current_episode: int = 0):
+        self.engine.reset()
+        return self._pack_obs(self._fetch())
+
+    def step_async(self, actions, num_current_episode=None):
+        eng = self.engine
+        B, N, A = self.num_envs, self.num_agents, self._A
+        if isinstance(actions, torch.Tensor) and actions.is_cuda:
+            if actions.dtype in (torch.int32, torch.int64) and tuple(actions.shape) == (B, N):
+                idx = actions.to(torch.int32)
+                self.h2d_bytes_last = 0
+            else:
+                idx = eng.decode_onehot(actions)
+                self.h2d_bytes_last = 0
+        else:
+            a = np.asarray(actions)
+            if a.shape == (B, N) and np.issubdtype(a.dtype, np.integer):  # index fast path
+                self._idx_pin.numpy()[...] = a
+                eng.action_idx.copy_(self._idx_pin, non_blocking=True)
+                idx = eng.action_idx
+                self.h2d_bytes_last = self._idx_pin.numel() * 4
+            else:
+                if a.shape != (B, N, A):
+                    raise ValueError(f"actions must have shape {(B, N, A)} (one-hot) or {(B, N)} (int), got {a.shape}")
+                w = 8 if a.dtype == np.float64 else 4
+                self._act_pin[w].numpy()[...] = a
+                self._act_dev[w].copy_(self._act_pin[w], non_blocking=True)
+                idx = eng.decode_onehot(self._act_dev[w])
+                self.h2d_bytes_last = a.size * w
+        eng.step(idx)
+        self.waiting = True
+
+    def step_wait(self):
+        o = self._fetch()
+        self.waiting = False
+        obs, ids, node_obs, adj = self._pack_obs(o)
+        collab = bool(self.cfg.flags & abi.FLAG_COLLABORATIVE)
+        if self.output == "torch":
+            rews = o["reward"].unsqueeze(-1) if collab else o["reward"]
+            dones = o["done"].bool()
+            infos = None
+            if "info" in o:
+                infos = {"info": o["info"], "individual_reward": o["indiv_reward"]}
+        else:
+            rews = o["reward"][..., None] if collab else o["reward"]  # [[sum]]*N -> (B,N,1), environment.py:1059
+            dones = o["done"].view(np.bool_)
+            infos = LazyInfos(o["info"], o["indiv_reward"]) if "info" in o else tuple([{}] * 0)
+        if self.returns_reset_count:
+            # env_wrappers.py:925-936: reset_count = 1 when any env auto-reset this step
+            if self.output == "torch":
+                rc = int(bool(dones.all(dim=1).any()))
+            else:
+                rc = int(bool(dones.all(axis=1).any()))
+            return obs, ids, node_obs, adj, rews, dones, infos, rc
+        return obs, ids, node_obs, adj, rews, dones, infos
+
+    def close(self):
+        if self.closed:
+            return
+        self.engine.close()
+        self.closed = True
+
+    # -- device-side statistics for the once-per-rollout reduction (dist.py) ---------------
+    def episode_stats(self) -> torch.Tensor:
+        """[sum reward, #agent collisions, #obstacle collisions, #agents done, #agents] of the
+        current step as a float64 device vector (reduced across GPUs by dist.reduce_stats)."""
+        o, st = self.engine.out, self.engine.state
+        cnt = st["agent_cnt"].to(torch.float64)
+        key = "indiv_reward" if "indiv_reward" in o else "reward"
+        return torch.stack([o[key].to(torch.float64).sum(), cnt[..., abi.AC_AGENT_COLL].sum(),
+                            cnt[..., abi.AC_OBST_COLL].sum(), o["done"].to(torch.float64).sum(),
+                            torch.tensor(float(self.num_envs * self.num_agents), dtype=torch.float64,
+                                         device=self.engine.device)])
+
+
+class GraphSubprocVecEnv(_BatchedVecEnv):
+    """env_wrappers.py:959-1037 -- step_wait returns 7 values."""
+    returns_reset_count = False
+
+
+class GraphDummyVecEnv(_BatchedVecEnv):
+    """env_wrappers.py:903-956 -- step_wait returns 8 values (adds reset_count)."""
+    returns_reset_count = True

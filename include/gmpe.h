@@ -201,6 +201,8 @@ typedef struct GmpeStepOut {
   int32_t* gnn_edge_index; /* i32 [B][2][edge_cap] process_adj (gnn_new.py:328-358), per world, strict < */
   void* gnn_edge_attr;     /* Real [B][edge_cap]                                                        */
   int32_t* gnn_num_edges;  /* i32 [B]                                                                   */
+  void* indiv_reward;      /* Real [B][N] reward before the collaborative sum: info['individual_reward']
+                                          (environment.py:1050)                                          */
 } GmpeStepOut;
 
 /* Teacher forcing for bit-parity runs.  NULL pointers = on-device Philox. */
@@ -248,6 +250,10 @@ int gmpe_step(gmpe_handle h, const GmpeState* st, const int32_t* action_idx,
  * onehot: [B][N][A] of float (elem_bytes 4) or double (8); first maximum wins. */
 int gmpe_decode_onehot(gmpe_handle h, const void* onehot, int elem_bytes,
                        int32_t* action_idx, void* cuda_stream);
+
+/* Re-key the Philox streams: replaces env.seed(seed) (environment.py:219-223, called by
+ * train_mpe.py:31 with seed + rank*1000); world_offset as in GmpeConfig. */
+int gmpe_set_seed(gmpe_handle h, uint64_t seed, int64_t world_offset);
 
 /* Number of kernel launches issued through this handle so far (bench gpu_launches). */
 int64_t gmpe_launch_count(gmpe_handle h);

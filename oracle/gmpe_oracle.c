@@ -919,6 +919,7 @@ static void step_world(World* w, const int32_t* act, const GmpeStepInject* inj, 
     for (int i = 0; i < N; ++i) sum += rew[i];
     for (int i = 0; i < N; ++i) r[i] = sum;
   } else for (int i = 0; i < N; ++i) r[i] = rew[i];
+  if (out->indiv_reward) for (int i = 0; i < N; ++i) ((double*)out->indiv_reward)[w->b * N + i] = rew[i]; /* env:1050 */
   write_graph_outputs(w, out);
   if ((c->flags & GMPE_FLAG_AUTO_RESET) && all_done) reset_world(w, inj, out); /* wrap:869-870 */
 }
