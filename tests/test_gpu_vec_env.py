@@ -1,0 +1,148 @@
+"""GPU tests of the reference-facing plugin surfaces: GraphSubprocVecEnv / GraphDummyVecEnv
+(onpolicy/envs/env_wrappers.py:903-1037) and MultiAgentGraphEnv (multiagent/environment.py:904)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Trace, traces
+from gmpe_b200 import abi, default_args, make_config
+from oracle.oracle import OracleEnv
+
+pytestmark = pytest.mark.gpu
+
+JULY = dict(scenario_name="nav_metered_one_goal_graph_rotate_tube_july", dynamics_type="air_taxi", world_size=3,
+            episode_length=6, goal_rew=30, collaborative=False, seed=3)
+
+
+def test_subproc_vec_env_reference_calling_convention_and_shapes():
+    from gmpe_b200.env_wrappers import GraphDummyVecEnv, GraphSubprocVecEnv
+    from gmpe_b200.environment import GraphMPEEnv
+
+    args = default_args(**JULY)
+
+    def get_env_fn(rank):  # onpolicy/scripts/train_mpe.py:22-33
+        def init_env():
+            env = GraphMPEEnv(args)
+            env.seed(args.seed + rank * 1000)
+            return env
+        return init_env
+
+    B, N, E, A = 5, 3, 6, 25
+    envs = GraphSubprocVecEnv([get_env_fn(i) for i in range(B)])
+    assert envs.num_envs == B and envs.action_space[0].n == A
+    assert envs.node_observation_space[0].shape == (E, 8) and envs.adj_observation_space[0].shape == (E, E)
+    obs, ag, node, adj = envs.reset()
+    assert obs.shape == (B, N, 19) and ag.shape == (B, N, 1) and node.shape == (B, N, E, 8) and adj.shape == (B, N, E, E)
+    assert (ag[:, :, 0] == np.arange(N)).all()
+    acts = np.eye(A)[np.random.RandomState(0).randint(A, size=(B, N))]  # graph_mpe_runner.py:375-377
+    out = envs.step(acts, 0)
+    assert len(out) == 7
+    obs, ag, node, adj, rews, dones, infos = out
+    assert rews.shape == (B, N) and dones.shape == (B, N) and dones.dtype == np.bool_
+    assert len(infos) == B and len(infos[0]) == N and "Dist_to_goal" in infos[0][0].keys()
+    assert infos[B - 1][N - 1]["individual_reward"] == rews[B - 1, N - 1]
+    assert (adj[:, 0] == adj[:, 1]).all() and (adj[:, 0] == adj[:, 2]).all()  # one matrix per world (G12)
+    with pytest.raises(ValueError):
+        envs.step(np.zeros((B, N, A + 1)), 0)
+    envs.close()
+
+    dummy = GraphDummyVecEnv([get_env_fn(0)])
+    dummy.reset()
+    o8 = dummy.step(np.eye(A)[np.zeros((1, N), dtype=int)], 0)
+    assert len(o8) == 8 and o8[7] in (0, 1)  # reset_count appended
+    dummy.close()
+
+
+@pytest.mark.parametrize("kw", [JULY, dict(scenario_name="navigation_graph", episode_length=5, num_obstacles=2, seed=9)])
+def test_vec_env_matches_oracle_through_host_one_hot_actions_with_auto_reset(kw):
+    from gmpe_b200.env_wrappers import GraphSubprocVecEnv
+
+    args = default_args(**kw)
+    B, T = 40, 14
+    envs = GraphSubprocVecEnv(args=args, num_envs=B, precision="fp64", seed=args.seed, env_edges=True)
+    cfg = envs.cfg
+    orc = OracleEnv(cfg, use_rk45=False)
+    N, A, E = cfg.num_agents, cfg.total_actions, envs.engine.E
+    o = orc.reset()
+    obs, ag, node, adj = envs.reset()
+    np.testing.assert_allclose(obs, o["obs"], atol=1e-9)
+    np.testing.assert_allclose(node, o["node_obs"], atol=1e-9)
+    rs = np.random.RandomState(1)
+    saw_reset = False
+    for t in range(T):
+        idx = rs.randint(A, size=(B, N))
+        o = orc.step(idx.astype(np.int32))
+        obs, ag, node, adj, rews, dones, infos = envs.step(np.eye(A)[idx], t)
+        np.testing.assert_allclose(obs, o["obs"], atol=1e-9)
+        np.testing.assert_allclose(node, o["node_obs"], atol=1e-9)
+        np.testing.assert_allclose(adj, np.broadcast_to(o["adj"][:, None], (B, N, E, E)), atol=1e-9)
+        want_r = o["reward"][..., None] if cfg.flags & abi.FLAG_COLLABORATIVE else o["reward"]
+        np.testing.assert_allclose(rews, want_r, atol=1e-9)
+        assert (dones == o["done"].astype(bool)).all()
+        np.testing.assert_allclose(np.array([[infos[e][a]["Min_time_to_goal"] for a in range(N)] for e in range(3)]),
+                                   o["info"][:3, :, abi.INFO_KEYS.index("Min_time_to_goal")], atol=1e-9)
+        if dones.all(axis=1).any():
+            saw_reset = True
+            e = int(np.argmax(dones.all(axis=1)))
+            # the observation of a finished env is the FIRST observation of its next episode
+            # (env_wrappers.py:867-873) while reward/done stay terminal
+            st = envs.engine.state["agent_state"][e].cpu().numpy()
+            col = (0, 1) if cfg.scenario == abi.SCEN_JULY_TUBE else (2, 3)
+            np.testing.assert_allclose(obs[e][:, col], st[:, :2], atol=1e-12)
+            assert int(envs.engine.state["world_i"][e, abi.WI_STEP]) == 0
+    assert saw_reset
+    envs.close()
+
+
+def test_vec_env_device_output_mode_is_zero_copy():
+    from gmpe_b200.env_wrappers import GraphSubprocVecEnv
+
+    args = default_args(**JULY)
+    envs = GraphSubprocVecEnv(args=args, num_envs=16, output="torch")
+    obs, ag, node, adj = envs.reset()
+    assert obs.is_cuda and node.is_cuda and adj.shape == (16, 3, 6, 6) and adj.stride(1) == 0
+    idx = torch.zeros((16, 3), dtype=torch.int32, device="cuda")
+    obs, ag, node, adj, rews, dones, infos = envs.step(idx, 0)
+    assert obs.data_ptr() == envs.engine.out["obs"].data_ptr() and dones.dtype == torch.bool
+    assert envs.h2d_bytes_last == 0
+    st = envs.episode_stats()
+    assert st.shape == (5,) and float(st[4]) == 48.0
+    envs.close()
+
+
+def test_multi_agent_graph_env_replays_a_golden_episode_through_the_scenario_api():
+    from gmpe_b200.environment import MultiAgentGraphEnv
+    from gmpe_b200.scenario import Scenario
+
+    tr = Trace([p for p in traces() if "n3_pursuit_s1" in p][0])
+    scenario = Scenario(precision="fp64")
+    world = scenario.make_world(tr.args)
+    env = MultiAgentGraphEnv(world=world, reset_callback=scenario.reset_world, reward_callback=scenario.reward,
+                             observation_callback=scenario.observation,
+                             graph_observation_callback=scenario.graph_observation, update_graph=scenario.update_graph,
+                             id_callback=scenario.get_id, info_callback=scenario.info_callback,
+                             done_callback=scenario.done, scenario_name=tr.args.scenario_name,
+                             dynamics_type=tr.args.dynamics_type)
+    assert env.n == 3 and env.action_space[0].n == 25 and env.observation_space[0].shape == (19,)
+    obs_n, id_n, node_n, adj_n = env.reset()
+    assert len(obs_n) == 3 and node_n[0].shape == (6, 8) and adj_n[0].shape == (6, 6)
+    z = tr.z
+    world.engine.reset(reset_state=tr.reset_state(0))  # teacher-forced initial condition of the trace
+    world.engine.state["agent_flags"][0, :, abi.AF_PREV_PHASE] = torch.as_tensor(z["init_prev_phase"][0], dtype=torch.uint8)
+    world._invalidate()
+    for t in range(60):
+        if not np.isnan(z["theta_draw"][t]).all():
+            break  # the B=1 env draws its own headings; stop before the first goal reach
+        obs_n, id_n, node_n, adj_n, rew_n, done_n, info_n = env.step([np.eye(25)[a] for a in z["actions"][t]])
+        np.testing.assert_allclose(np.array(obs_n), z["obs"][t], atol=2e-7)
+        np.testing.assert_allclose(np.array(node_n), z["node_obs"][t], atol=2e-7)
+        np.testing.assert_allclose(adj_n[0], z["adj"][t], atol=2e-7)
+        np.testing.assert_allclose(np.array(rew_n), z["reward"][t], atol=2e-7)
+        assert done_n == list(z["done"][t])
+        assert info_n[1]["individual_reward"] == rew_n[1] and "Num_agent_collisions" in info_n[0]
+        assert (world.edge_list == z["edge_index"][t][:, :z["num_edges"][t]]).all()
+        assert [int(i[0]) for i in id_n] == [0, 1, 2]
+    assert t > 10
+    with pytest.raises(AssertionError):
+        env.step([np.eye(24)[0]] * 3)
+    env.close()
