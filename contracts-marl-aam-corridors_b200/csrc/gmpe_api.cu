@@ -19,6 +19,7 @@ struct gmpe_ctx {
   int num_tiles;
   int grid;
   size_t smem_bytes;
+  int stage_graph;
   int64_t launches;
   std::string err;
 };
@@ -58,10 +59,20 @@ static void plan_tiles(const GmpeConfig& c, int threads, int* wpb, int* tiles) {
 }
 
 template <typename Real>
-static size_t smem_for(const GmpeConfig& c, int wpb) {
+static size_t smem_for(const GmpeConfig& c, int wpb, int stage_graph) {
   int E = c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls;
   int F = c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
-  return smem_layout<Real>(wpb, c.num_agents, E, c.num_walls, F, nullptr, nullptr);
+  return smem_layout<Real>(wpb, c.num_agents, E, c.num_walls, F, stage_graph, nullptr, nullptr);
+}
+
+// Small worlds stage the adjacency matrix and the padded edge buffers of a tile in shared
+// memory (thread-per-world compaction, 128-bit stores); large worlds generate in place.
+static int pick_stage_graph(const GmpeConfig& c, int wpb) {
+  int E = c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls;
+  if (E > 12) return 0;
+  int mode = (c.flags & GMPE_FLAG_GNN_EDGES) ? 3 : 1;
+  size_t need = c.precision == GMPE_F64 ? smem_for<double>(c, wpb, mode) : smem_for<float>(c, wpb, mode);
+  return need <= 72 * 1024 ? mode : 0;
 }
 
 extern "C" {
@@ -119,7 +130,8 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
   h->threads = 256;
   plan_tiles(h->cfg, h->threads, &h->wpb, &h->num_tiles);
   const bool f64 = cfg->precision == GMPE_F64;
-  h->smem_bytes = f64 ? smem_for<double>(h->cfg, h->wpb) : smem_for<float>(h->cfg, h->wpb);
+  h->stage_graph = pick_stage_graph(h->cfg, h->wpb);
+  h->smem_bytes = f64 ? smem_for<double>(h->cfg, h->wpb, h->stage_graph) : smem_for<float>(h->cfg, h->wpb, h->stage_graph);
   const void* fn = f64 ? (const void*)gmpe_step_kernel<double> : (const void*)gmpe_step_kernel<float>;
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -187,6 +199,7 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   p.mode = mode;
   p.wpb = h->wpb;
   p.num_tiles = h->num_tiles;
+  p.stage_graph = h->stage_graph;
   const int N = c.num_agents, L = c.num_landmarks, O = c.num_obstacles, W = c.num_walls;
   p.E = N + L + O + W;
   p.F = c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;

@@ -41,78 +41,124 @@ struct KParams {
   int wpb;        // worlds per tile
   int num_tiles;
   int E, F;       // entities per world, obs width
+  int stage_graph; // small worlds: adjacency / edges staged in shared memory (see Smem)
   FastDiv dN, dE, dL, dO, dW, dF, d16, dE2, dNE2, dEE;
 };
 
 // ---- shared memory carve-up --------------------------------------------------------
 template <typename Real>
 struct Smem {
+  // -- live for the whole tile
   typename RT<Real>::V2* pos;      // [WPB*E]   post-step positions of every entity
   typename RT<Real>::V2* velpre;   // [WPB*N]   p_vel before reward()
   typename RT<Real>::V2* velpost;  // [WPB*N]   p_vel after reward() (heading re-draw on goal reach)
-  typename RT<Real>::V4* nst;      // [WPB*N]   reset: freshly placed agent states
   Real* wf;                        // [WPB*16]
   Real* wl;                        // [WPB*W*4]
+  int32_t* wstep;                  // [WPB]
+  int32_t* wep;                    // [WPB]
+  uint8_t* stpre;                  // [WPB*N]
+  uint8_t* stpost;                 // [WPB*N]
+  uint8_t* mask;                   // [WPB*E]   entity disconnected from the graph
+  uint8_t* wreset;                 // [WPB]
+  uint8_t* wwrite;                 // [WPB]
+  // -- phase-A scratch (dead once obs has left the SM) ...
+  typename RT<Real>::V4* nst;      // [WPB*N]   reset: freshly placed agent states
   Real* obs;                       // [WPB*N*F] staging
   Real* rew;                       // [WPB*N]
   Real* sperr;                     // [WPB*N]
   int32_t* cold;                   // [WPB*N*3] info counters before this step
   int32_t* cnew;                   // [WPB*N*3] ... after
-  int32_t* wstep;                  // [WPB]
-  int32_t* wep;                    // [WPB]
-  uint8_t* stpre;                  // [WPB*N]
-  uint8_t* stpost;                 // [WPB*N]
   uint8_t* done;                   // [WPB*N]
-  uint8_t* wreset;                 // [WPB]
-  uint8_t* wwrite;                 // [WPB]
+  // -- ... aliased by the phase-B staging of small worlds (KParams::stage_graph)
+  Real* adjs;                      // [WPB*E*E]
+  int32_t* eidx;                   // [WPB*2*cap]
+  Real* eattr;                     // [WPB*cap]
+  int32_t* gidx;                   // [WPB*2*cap]
+  Real* gattr;                     // [WPB*cap]
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// stage_graph: 0 none, bit0 adjacency + env edges, bit1 gnn edges as well
 template <typename Real>
-__host__ __device__ inline size_t smem_layout(int wpb, int N, int E, int W, int F, Smem<Real>* s, unsigned char* base) {
+__host__ __device__ inline size_t smem_layout(int wpb, int N, int E, int W, int F, int stage_graph, Smem<Real>* s, unsigned char* base) {
   size_t o = 0;
   auto take = [&](size_t bytes, size_t al) { o = align_up(o, al); size_t r = o; o += bytes; return r; };
-  size_t R = sizeof(Real);
+  const size_t R = sizeof(Real);
+  const size_t cap = (size_t)E * (E - 1);
   size_t o_pos = take(2 * R * wpb * E, 16);
   size_t o_vpre = take(2 * R * wpb * N, 16);
   size_t o_vpost = take(2 * R * wpb * N, 16);
-  size_t o_nst = take(4 * R * wpb * N, 32);
   size_t o_wf = take(R * wpb * GMPE_WORLD_F, 16);
   size_t o_wl = take(R * wpb * (W > 0 ? W : 1) * GMPE_WALL_F, 16);
+  size_t o_wstep = take(4 * wpb, 16);
+  size_t o_wep = take(4 * wpb, 16);
+  size_t o_stpre = take(wpb * N, 16);
+  size_t o_stpost = take(wpb * N, 16);
+  size_t o_mask = take(wpb * E, 16);
+  size_t o_wreset = take(wpb, 16);
+  size_t o_wwrite = take(wpb, 16);
+  o = align_up(o, 32);
+  const size_t scratch0 = o;
+  size_t o_nst = take(4 * R * wpb * N, 32);
   size_t o_obs = take(R * wpb * N * F, 16);
   size_t o_rew = take(R * wpb * N, 16);
   size_t o_sp = take(R * wpb * N, 16);
   size_t o_cold = take(4 * wpb * N * 3, 16);
   size_t o_cnew = take(4 * wpb * N * 3, 16);
-  size_t o_wstep = take(4 * wpb, 16);
-  size_t o_wep = take(4 * wpb, 16);
-  size_t o_stpre = take(wpb * N, 16);
-  size_t o_stpost = take(wpb * N, 16);
   size_t o_done = take(wpb * N, 16);
-  size_t o_wreset = take(wpb, 16);
-  size_t o_wwrite = take(wpb, 16);
+  const size_t scratch_end = o;
+  o = scratch0;
+  size_t o_adjs = 0, o_eidx = 0, o_eattr = 0, o_gidx = 0, o_gattr = 0;
+  if (stage_graph) {
+    o_adjs = take(R * wpb * E * E, 16);
+    o_eidx = take(4 * wpb * 2 * cap, 16);
+    o_eattr = take(R * wpb * cap, 16);
+    if (stage_graph & 2) {
+      o_gidx = take(4 * wpb * 2 * cap, 16);
+      o_gattr = take(R * wpb * cap, 16);
+    }
+  }
+  if (o < scratch_end) o = scratch_end;
   if (s) {
     s->pos = (typename RT<Real>::V2*)(base + o_pos);
     s->velpre = (typename RT<Real>::V2*)(base + o_vpre);
     s->velpost = (typename RT<Real>::V2*)(base + o_vpost);
-    s->nst = (typename RT<Real>::V4*)(base + o_nst);
     s->wf = (Real*)(base + o_wf);
     s->wl = (Real*)(base + o_wl);
+    s->wstep = (int32_t*)(base + o_wstep);
+    s->wep = (int32_t*)(base + o_wep);
+    s->stpre = base + o_stpre;
+    s->stpost = base + o_stpost;
+    s->mask = base + o_mask;
+    s->wreset = base + o_wreset;
+    s->wwrite = base + o_wwrite;
+    s->nst = (typename RT<Real>::V4*)(base + o_nst);
     s->obs = (Real*)(base + o_obs);
     s->rew = (Real*)(base + o_rew);
     s->sperr = (Real*)(base + o_sp);
     s->cold = (int32_t*)(base + o_cold);
     s->cnew = (int32_t*)(base + o_cnew);
-    s->wstep = (int32_t*)(base + o_wstep);
-    s->wep = (int32_t*)(base + o_wep);
-    s->stpre = base + o_stpre;
-    s->stpost = base + o_stpost;
     s->done = base + o_done;
-    s->wreset = base + o_wreset;
-    s->wwrite = base + o_wwrite;
+    s->adjs = (Real*)(base + o_adjs);
+    s->eidx = (int32_t*)(base + o_eidx);
+    s->eattr = (Real*)(base + o_eattr);
+    s->gidx = (int32_t*)(base + o_gidx);
+    s->gattr = (Real*)(base + o_gattr);
   }
   return align_up(o, 16);
+}
+
+// contiguous shared -> global copy of n elements as 128-bit vectors (+ scalar tail);
+// dst must be 16-byte aligned (tiles start on multiples of 4 worlds)
+template <typename T>
+__device__ __forceinline__ void copy_out(T* __restrict__ dst, const T* __restrict__ src, int n, int tid, int nthr) {
+  constexpr int VW = 16 / sizeof(T);
+  const int nv = n / VW;
+  const int4* s4 = (const int4*)src;
+  int4* d4 = (int4*)dst;
+  for (int q = tid; q < nv; q += nthr) d4[q] = s4[q];
+  for (int q = nv * VW + tid; q < n; q += nthr) dst[q] = src[q];
 }
 
 // ---- per-agent pieces --------------------------------------------------------------
@@ -291,7 +337,7 @@ __device__ __forceinline__ void july_obs(const typename RT<Real>::V2* pos_w, con
 // ---- reset (thread 0 of a world): random_scenario + setup_tube_params (july:440-613),
 // set_landmarks_in_point (utils.py:165-193); nav placement is defined-by-build
 template <typename Real>
-__device__ void place_world(const KParams& p, const Smem<Real>& sm, int lw, int64_t b) {
+__device__ __noinline__ void place_world(const KParams& p, const Smem<Real>& sm, int lw, int64_t b) {
   const GmpeConfig& c = p.c;
   const int N = c.num_agents, L = c.num_landmarks, O = c.num_obstacles, W = c.num_walls, E = p.E;
   typename RT<Real>::V2* pos_w = sm.pos + lw * E;
@@ -391,7 +437,7 @@ __global__ void __launch_bounds__(256) gmpe_step_kernel(const __grid_constant__ 
   const bool do_info = (c.flags & GMPE_FLAG_INFO) != 0;
   const int tid = threadIdx.x, nthr = blockDim.x;
   Smem<Real> sm;
-  smem_layout<Real>(WPB, N, E, W, F, &sm, smem_raw);
+  smem_layout<Real>(WPB, N, E, W, F, p.stage_graph, &sm, smem_raw);
 
   Real* g_as = (Real*)p.st.agent_state;
   Real* g_aux = (Real*)p.st.agent_aux;
@@ -794,18 +840,19 @@ __global__ void __launch_bounds__(256) gmpe_step_kernel(const __grid_constant__ 
     __syncthreads();
 
     // ---------------- phase B: element-parallel output generation -------------------------
+    // disconnected mask per entity (july:1627-1648): done agents, and landmark l once agent l
+    // reached it (goal_tracker[l] == l; goal_match_index = arange)
+    for (int q = tid; q < nw * E; q += nthr) {
+      uint32_t w, k; p.dE.divmod(q, w, k);
+      const uint8_t* stw = sm.stpost + w * N;
+      sm.mask[q] = k < (uint32_t)N ? stw[k] : ((k < (uint32_t)(2 * N) && k < (uint32_t)(N + L)) ? stw[k - N] : (uint8_t)0);
+    }
     // obs: staged rows -> contiguous 128-bit stores
     if (p.out.obs) {
       Real* g_obs = (Real*)p.out.obs + (size_t)w0 * N * F;
       const int total = nw * N * F;
       if (p.mode == MODE_STEP) {
-        constexpr int VW = 16 / sizeof(Real);
-        const int nv = total / VW;
-        using VV = typename std::conditional<sizeof(Real) == 4, float4, double2>::type;
-        const VV* src = (const VV*)sm.obs;
-        VV* dst = (VV*)g_obs;
-        for (int q = tid; q < nv; q += nthr) dst[q] = src[q];
-        for (int q = nv * VW + tid; q < total; q += nthr) g_obs[q] = sm.obs[q];
+        copy_out<Real>(g_obs, sm.obs, total, tid, nthr);
       } else {
         for (int q = tid; q < total; q += nthr) {
           uint32_t row = p.dF.div(q);
@@ -843,80 +890,133 @@ __global__ void __launch_bounds__(256) gmpe_step_kernel(const __grid_constant__ 
         ((V4*)g_node)[q] = v;
       }
     }
-    // adj: masked distance matrix, one copy per world (july:1625-1648)
-    if (p.out.adj) {
-      Real* g_adj = (Real*)p.out.adj + (size_t)w0 * E * E;
-      const int total = nw * E * E;
-      for (int q = tid; q < total; q += nthr) {
+    __syncthreads();  // mask ready; phase-A scratch (obs staging, counters) is dead from here on
+
+    const bool env_e = (c.flags & GMPE_FLAG_ENV_EDGES) && p.out.edge_index;
+    const bool gnn_e = (c.flags & GMPE_FLAG_GNN_EDGES) && p.out.gnn_edge_index;
+    const int cap = E * (E - 1), EE = E * E;
+    const Real thr_env = Real(c.coordination_range);
+    const float thr_gnn = (float)c.gnn_max_edge_dist;
+    if (p.stage_graph && p.mode == MODE_STEP) {
+      // ---- small worlds: the masked distance matrix of the tile is built ONCE in shared
+      // memory; adj is a vector copy of it and the edge lists are compacted from it
+      // (one thread per world walks its E*E entries in row-major order) into staged,
+      // pre-padded buffers that leave the SM as contiguous 128-bit stores.
+      for (int q = tid; q < nw * EE; q += nthr) {
         uint32_t w, rc, r, cc;
         p.dEE.divmod(q, w, rc);
         p.dE.divmod(rc, r, cc);
-        if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
         const V2* pw = sm.pos + w * E;
-        const uint8_t* stw = sm.stpost + w * N;
-        bool mr = r < (uint32_t)N ? stw[r] : (r < (uint32_t)(2 * N) && r < (uint32_t)(N + L) ? stw[r - N] : 0);
-        bool mc = cc < (uint32_t)N ? stw[cc] : (cc < (uint32_t)(2 * N) && cc < (uint32_t)(N + L) ? stw[cc - N] : 0);
+        const uint8_t* mk = sm.mask + w * E;
         V2 a = pw[r], bb = pw[cc];
-        Real d = (r == cc || mr || mc) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
-        g_adj[q] = d;
+        sm.adjs[q] = (r == cc || mk[r] || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
       }
-    }
-    // edges: warp-per-world stream compaction (ballot + popc) into the padded buffers
-    const bool env_e = (c.flags & GMPE_FLAG_ENV_EDGES) && p.out.edge_index;
-    const bool gnn_e = (c.flags & GMPE_FLAG_GNN_EDGES) && p.out.gnn_edge_index;
-    if (env_e || gnn_e) {
-      const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-      const int cap = E * (E - 1), EE = E * E;
-      const Real thr_env = Real(c.coordination_range);
-      const float thr_gnn = (float)c.gnn_max_edge_dist;
-      for (int w = warp; w < nw; w += nwarps) {
-        if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
-        const V2* pw = sm.pos + w * E;
-        const uint8_t* stw = sm.stpost + w * N;
-        const size_t gb = (size_t)(w0 + w);
-        int32_t* ei = env_e ? p.out.edge_index + gb * 2 * cap : nullptr;
-        Real* ea = env_e ? (Real*)p.out.edge_attr + gb * cap : nullptr;
-        int32_t* gi = gnn_e ? p.out.gnn_edge_index + gb * 2 * cap : nullptr;
-        Real* gea = gnn_e ? (Real*)p.out.gnn_edge_attr + gb * cap : nullptr;
-        int n_env = 0, n_gnn = 0;
-        for (int base = 0; base < EE; base += 32) {
-          int q = base + lane;
-          uint32_t r = 0, cc = 0;
-          Real d = Real(0);
-          if (q < EE) {
-            p.dE.divmod(q, r, cc);
-            bool mr = r < (uint32_t)N ? stw[r] : (r < (uint32_t)(2 * N) && r < (uint32_t)(N + L) ? stw[r - N] : 0);
-            bool mc = cc < (uint32_t)N ? stw[cc] : (cc < (uint32_t)(2 * N) && cc < (uint32_t)(N + L) ? stw[cc - N] : 0);
-            V2 a = pw[r], bb = pw[cc];
-            d = (r == cc || mr || mc) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
+      if (env_e) {
+        for (int q = tid; q < nw * 2 * cap; q += nthr) sm.eidx[q] = -1;
+        for (int q = tid; q < nw * cap; q += nthr) sm.eattr[q] = Real(0);
+      }
+      if (gnn_e) {
+        for (int q = tid; q < nw * 2 * cap; q += nthr) sm.gidx[q] = -1;
+        for (int q = tid; q < nw * cap; q += nthr) sm.gattr[q] = Real(0);
+      }
+      __syncthreads();
+      if (p.out.adj) copy_out<Real>((Real*)p.out.adj + (size_t)w0 * EE, sm.adjs, nw * EE, tid, nthr);
+      if ((env_e || gnn_e) && tid < nw) {
+        const int w = tid;
+        const Real* aw = sm.adjs + w * EE;
+        int32_t* ei = sm.eidx + w * 2 * cap; Real* ea = sm.eattr + w * cap;
+        int32_t* gi = sm.gidx + w * 2 * cap; Real* ga_ = sm.gattr + w * cap;
+        int n_env = 0, n_gnn = 0, r = 0, cc = 0;
+        for (int q = 0; q < EE; ++q) {
+          Real d = aw[q];
+          if (env_e && d > Real(0) && d <= thr_env) {  // update_graph (july:1660-1665), row-major
+            ei[n_env] = r; ei[cap + n_env] = cc; ea[n_env] = d; ++n_env;
           }
-          if (env_e) {  // update_graph: (d <= max_edge_dist) & (d > 0), row-major (july:1660-1665)
-            bool on = d > Real(0) && d <= thr_env;
-            unsigned m = __ballot_sync(0xffffffffu, on);
-            if (on) {
-              int slot = n_env + __popc(m & ((1u << lane) - 1));
-              ei[slot] = (int32_t)r; ei[cap + slot] = (int32_t)cc; ea[slot] = d;
-            }
-            n_env += __popc(m);
-          }
-          if (gnn_e) {  // process_adj on the fp32 cast: (adj < max_edge_dist) & (adj > 0) (gnn_new.py:339)
+          if (gnn_e) {  // process_adj on the fp32 cast (gnn_new.py:339): strict <
             float df = (float)d;
-            bool on = df > 0.0f && df < thr_gnn;
-            unsigned m = __ballot_sync(0xffffffffu, on);
-            if (on) {
-              int slot = n_gnn + __popc(m & ((1u << lane) - 1));
-              gi[slot] = (int32_t)r; gi[cap + slot] = (int32_t)cc; gea[slot] = Real(df);
-            }
-            n_gnn += __popc(m);
+            if (df > 0.0f && df < thr_gnn) { gi[n_gnn] = r; gi[cap + n_gnn] = cc; ga_[n_gnn] = Real(df); ++n_gnn; }
           }
+          if (++cc == E) { cc = 0; ++r; }
         }
-        if (env_e) {
-          for (int q = n_env + lane; q < cap; q += 32) { ei[q] = -1; ei[cap + q] = -1; ea[q] = Real(0); }
-          if (lane == 0) p.out.num_edges[gb] = n_env;
+        if (env_e) p.out.num_edges[w0 + w] = n_env;
+        if (gnn_e) p.out.gnn_num_edges[w0 + w] = n_gnn;
+      }
+      __syncthreads();
+      if (env_e) {
+        copy_out<int32_t>(p.out.edge_index + (size_t)w0 * 2 * cap, sm.eidx, nw * 2 * cap, tid, nthr);
+        copy_out<Real>((Real*)p.out.edge_attr + (size_t)w0 * cap, sm.eattr, nw * cap, tid, nthr);
+      }
+      if (gnn_e) {
+        copy_out<int32_t>(p.out.gnn_edge_index + (size_t)w0 * 2 * cap, sm.gidx, nw * 2 * cap, tid, nthr);
+        copy_out<Real>((Real*)p.out.gnn_edge_attr + (size_t)w0 * cap, sm.gattr, nw * cap, tid, nthr);
+      }
+    } else {
+      // ---- large worlds (or reset-only launches): generate in place
+      // adj: masked distance matrix, one copy per world (july:1625-1648)
+      if (p.out.adj) {
+        Real* g_adj = (Real*)p.out.adj + (size_t)w0 * EE;
+        const int total = nw * EE;
+        for (int q = tid; q < total; q += nthr) {
+          uint32_t w, rc, r, cc;
+          p.dEE.divmod(q, w, rc);
+          p.dE.divmod(rc, r, cc);
+          if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
+          const V2* pw = sm.pos + w * E;
+          const uint8_t* mk = sm.mask + w * E;
+          V2 a = pw[r], bb = pw[cc];
+          g_adj[q] = (r == cc || mk[r] || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
         }
-        if (gnn_e) {
-          for (int q = n_gnn + lane; q < cap; q += 32) { gi[q] = -1; gi[cap + q] = -1; gea[q] = Real(0); }
-          if (lane == 0) p.out.gnn_num_edges[gb] = n_gnn;
+      }
+      // edges: warp-per-world stream compaction (ballot + popc) into the padded buffers
+      if (env_e || gnn_e) {
+        const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+        for (int w = warp; w < nw; w += nwarps) {
+          if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
+          const V2* pw = sm.pos + w * E;
+          const uint8_t* mk = sm.mask + w * E;
+          const size_t gb = (size_t)(w0 + w);
+          int32_t* ei = env_e ? p.out.edge_index + gb * 2 * cap : nullptr;
+          Real* ea = env_e ? (Real*)p.out.edge_attr + gb * cap : nullptr;
+          int32_t* gi = gnn_e ? p.out.gnn_edge_index + gb * 2 * cap : nullptr;
+          Real* gea = gnn_e ? (Real*)p.out.gnn_edge_attr + gb * cap : nullptr;
+          int n_env = 0, n_gnn = 0;
+          for (int base = 0; base < EE; base += 32) {
+            int q = base + lane;
+            uint32_t r = 0, cc = 0;
+            Real d = Real(0);
+            if (q < EE) {
+              p.dE.divmod(q, r, cc);
+              V2 a = pw[r], bb = pw[cc];
+              d = (r == cc || mk[r] || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
+            }
+            if (env_e) {  // update_graph: (d <= max_edge_dist) & (d > 0), row-major (july:1660-1665)
+              bool on = d > Real(0) && d <= thr_env;
+              unsigned m = __ballot_sync(0xffffffffu, on);
+              if (on) {
+                int slot = n_env + __popc(m & ((1u << lane) - 1));
+                ei[slot] = (int32_t)r; ei[cap + slot] = (int32_t)cc; ea[slot] = d;
+              }
+              n_env += __popc(m);
+            }
+            if (gnn_e) {  // process_adj on the fp32 cast: (adj < max_edge_dist) & (adj > 0) (gnn_new.py:339)
+              float df = (float)d;
+              bool on = df > 0.0f && df < thr_gnn;
+              unsigned m = __ballot_sync(0xffffffffu, on);
+              if (on) {
+                int slot = n_gnn + __popc(m & ((1u << lane) - 1));
+                gi[slot] = (int32_t)r; gi[cap + slot] = (int32_t)cc; gea[slot] = Real(df);
+              }
+              n_gnn += __popc(m);
+            }
+          }
+          if (env_e) {
+            for (int q = n_env + lane; q < cap; q += 32) { ei[q] = -1; ei[cap + q] = -1; ea[q] = Real(0); }
+            if (lane == 0) p.out.num_edges[gb] = n_env;
+          }
+          if (gnn_e) {
+            for (int q = n_gnn + lane; q < cap; q += 32) { gi[q] = -1; gi[cap + q] = -1; gea[q] = Real(0); }
+            if (lane == 0) p.out.gnn_num_edges[gb] = n_gnn;
+          }
         }
       }
     }
