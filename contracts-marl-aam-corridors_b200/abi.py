@@ -125,7 +125,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("GMPE_LIB") or LIB_PATH  # GMPE_LIB: tuning variants (tools/sweep.py)
     if not os.path.exists(p):
         raise GmpeError(
             f"CUDA extension not built: {p} is missing. Run `python -c 'import __graft_entry__ as g; g.build()'` "

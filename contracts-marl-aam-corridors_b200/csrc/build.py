@@ -32,16 +32,22 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
-        return OUT
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines: tuple = ()) -> str:
+    """defines: extra -D flags (tuning variants built by tools/sweep.py go to `out`)."""
+    global OUT
+    if out is not None:
+        OUT_local = out
+    else:
+        OUT_local = OUT
+        if not force and not is_stale():
+            return OUT
     cmd = [
         nvcc_path(), "-std=c++17", "-O3", "-lineinfo",
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
         "-Xptxas", "-v" if verbose else "-O3",
-        "-o", OUT,
-    ] + [os.path.join(HERE, s) for s in SOURCES]
+        "-o", OUT_local,
+    ] + [f"-D{d}" for d in defines] + [os.path.join(HERE, s) for s in SOURCES]
     env = dict(os.environ)
     if os.path.exists("/usr/bin/g++"):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
@@ -50,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stderr[-4000:])
-    return OUT
+    return OUT_local
 
 
 if __name__ == "__main__":

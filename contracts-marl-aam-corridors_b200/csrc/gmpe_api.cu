@@ -1,6 +1,7 @@
 // gmpe_api.cu -- C ABI (include/gmpe.h) over the fused step kernel.
 // Built by csrc/build.py:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -shared
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -127,7 +128,11 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
   cudaGetDevice(&prev);
   cudaSetDevice(device);
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
-  h->threads = 256;
+  h->threads = GMPE_LB_THREADS;
+  if (const char* t = getenv("GMPE_THREADS")) {  // tuning knob (tools/sweep.py); must not exceed the launch bound
+    int v = atoi(t);
+    if (v >= 32 && v <= GMPE_LB_THREADS && v % 32 == 0) h->threads = v;
+  }
   plan_tiles(h->cfg, h->threads, &h->wpb, &h->num_tiles);
   const bool f64 = cfg->precision == GMPE_F64;
   h->stage_graph = pick_stage_graph(h->cfg, h->wpb);

@@ -424,8 +424,16 @@ __device__ __noinline__ void place_world(const KParams& p, const Smem<Real>& sm,
 }
 
 // ---- the kernel ----------------------------------------------------------------------
+// Launch bounds picked by tools/sweep.py on a B200 (profiles/r1_sweep.txt): 128 threads with
+// >= 6 resident CTAs per SM (<= 85 registers) beat 256 x 1..4 on every workload measured.
+#ifndef GMPE_LB_THREADS
+#define GMPE_LB_THREADS 128
+#endif
+#ifndef GMPE_LB_MINBLOCKS
+#define GMPE_LB_MINBLOCKS 6
+#endif
 template <typename Real>
-__global__ void __launch_bounds__(256) gmpe_step_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_kernel(const __grid_constant__ KParams p) {
   using V2 = typename RT<Real>::V2;
   using V4 = typename RT<Real>::V4;
   extern __shared__ __align__(32) unsigned char smem_raw[];
