@@ -52,9 +52,25 @@ static const char* validate(const GmpeConfig& c) {
   return nullptr;
 }
 
+static int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+// Worlds per tile: as many as the CTA has (world, agent) threads for, rounded down to the
+// multiple that keeps every tile's output slab 16-byte aligned (obs N*F, adj E*E, edges
+// E*(E-1) elements per world) when that is possible; copy_out falls back to scalar stores
+// otherwise.
 static void plan_tiles(const GmpeConfig& c, int threads, int* wpb, int* tiles) {
-  int w = (threads / c.num_agents) & ~3;  // multiple of 4: every tile's output slab starts 16-byte aligned
-  if (w < 4) w = 4;
+  const int E = c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls;
+  const int F = c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
+  const int vw = c.precision == GMPE_F64 ? 2 : 4;  // elements per 16 bytes
+  int m = 1;
+  const int counts[3] = {c.num_agents * F, E * E, E * (E - 1)};
+  for (int k = 0; k < 3; ++k) {
+    int need = vw / gcd_i(vw, counts[k]);
+    m = m * need / gcd_i(m, need);
+  }
+  int w = threads / c.num_agents;
+  if (w < 1) w = 1;
+  if (w >= m) w -= w % m;
   *wpb = w;
   *tiles = (c.num_worlds + w - 1) / w;
 }

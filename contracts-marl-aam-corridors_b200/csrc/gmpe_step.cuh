@@ -149,12 +149,12 @@ __host__ __device__ inline size_t smem_layout(int wpb, int N, int E, int W, int 
   return align_up(o, 16);
 }
 
-// contiguous shared -> global copy of n elements as 128-bit vectors (+ scalar tail);
-// dst must be 16-byte aligned (tiles start on multiples of 4 worlds)
+// contiguous shared -> global copy of n elements as 128-bit vectors (+ scalar tail) when both
+// ends are 16-byte aligned (plan_tiles picks a tile size that makes every slab aligned)
 template <typename T>
 __device__ __forceinline__ void copy_out(T* __restrict__ dst, const T* __restrict__ src, int n, int tid, int nthr) {
   constexpr int VW = 16 / sizeof(T);
-  const int nv = n / VW;
+  const int nv = (((size_t)dst | (size_t)src) & 15) ? 0 : n / VW;  // unaligned slab: scalar stores
   const int4* s4 = (const int4*)src;
   int4* d4 = (int4*)dst;
   for (int q = tid; q < nv; q += nthr) d4[q] = s4[q];
