@@ -7,6 +7,7 @@
 #include <new>
 #include <string>
 
+#include "gmpe_small.cuh"
 #include "gmpe_step.cuh"
 
 using namespace gmpe;
@@ -21,6 +22,8 @@ struct gmpe_ctx {
   int grid;
   size_t smem_bytes;
   int stage_graph;
+  int small;  // 1: thread-per-world kernel (gmpe_small.cuh), 0: tile kernel (gmpe_step.cuh)
+  const void* fn;
   int64_t launches;
   std::string err;
 };
@@ -92,6 +95,13 @@ static int pick_stage_graph(const GmpeConfig& c, int wpb) {
   return need <= 72 * 1024 ? mode : 0;
 }
 
+// Worlds with N = L = 3 and no obstacles / walls (BASELINE configs 1-3) run on the
+// thread-per-world kernel; GMPE_FORCE_TILE=1 keeps them on the tile kernel (A/B tests).
+static bool small_world_kernel(const GmpeConfig& c) {
+  if (const char* t = getenv("GMPE_FORCE_TILE")) if (atoi(t)) return false;
+  return c.num_agents == 3 && c.num_landmarks == 3 && c.num_obstacles == 0 && c.num_walls == 0;
+}
+
 extern "C" {
 
 int gmpe_abi_version(void) { return GMPE_ABI_VERSION; }
@@ -144,16 +154,36 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
   cudaGetDevice(&prev);
   cudaSetDevice(device);
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
-  h->threads = GMPE_LB_THREADS;
-  if (const char* t = getenv("GMPE_THREADS")) {  // tuning knob (tools/sweep.py); must not exceed the launch bound
-    int v = atoi(t);
-    if (v >= 32 && v <= GMPE_LB_THREADS && v % 32 == 0) h->threads = v;
-  }
-  plan_tiles(h->cfg, h->threads, &h->wpb, &h->num_tiles);
   const bool f64 = cfg->precision == GMPE_F64;
-  h->stage_graph = pick_stage_graph(h->cfg, h->wpb);
-  h->smem_bytes = f64 ? smem_for<double>(h->cfg, h->wpb, h->stage_graph) : smem_for<float>(h->cfg, h->wpb, h->stage_graph);
-  const void* fn = f64 ? (const void*)gmpe_step_kernel<double> : (const void*)gmpe_step_kernel<float>;
+  const bool july = cfg->scenario == GMPE_SCEN_JULY_TUBE;
+  h->small = small_world_kernel(h->cfg) ? 1 : 0;
+  int units = 0;  // CTAs needed to cover the batch once
+  if (h->small) {
+    // one thread per world, warps are independent: see gmpe_small.cuh
+    h->threads = 32 * GMPE_SMALL_WARPS;
+    h->wpb = h->threads;
+    h->num_tiles = (cfg->num_worlds + h->wpb - 1) / h->wpb;
+    h->stage_graph = 0;
+    if (f64) {
+      h->fn = july ? (const void*)gmpe_step_small_kernel<double, GMPE_SCEN_JULY_TUBE, 3> : (const void*)gmpe_step_small_kernel<double, GMPE_SCEN_NAV_GRAPH, 3>;
+      h->smem_bytes = GMPE_SMALL_WARPS * (july ? SmallTraits<double, GMPE_SCEN_JULY_TUBE, 3>::SLAB_BYTES : SmallTraits<double, GMPE_SCEN_NAV_GRAPH, 3>::SLAB_BYTES);
+    } else {
+      h->fn = july ? (const void*)gmpe_step_small_kernel<float, GMPE_SCEN_JULY_TUBE, 3> : (const void*)gmpe_step_small_kernel<float, GMPE_SCEN_NAV_GRAPH, 3>;
+      h->smem_bytes = GMPE_SMALL_WARPS * (july ? SmallTraits<float, GMPE_SCEN_JULY_TUBE, 3>::SLAB_BYTES : SmallTraits<float, GMPE_SCEN_NAV_GRAPH, 3>::SLAB_BYTES);
+    }
+  } else {
+    h->threads = GMPE_LB_THREADS;
+    if (const char* t = getenv("GMPE_THREADS")) {  // tuning knob (tools/sweep.py); must not exceed the launch bound
+      int v = atoi(t);
+      if (v >= 32 && v <= GMPE_LB_THREADS && v % 32 == 0) h->threads = v;
+    }
+    plan_tiles(h->cfg, h->threads, &h->wpb, &h->num_tiles);
+    h->stage_graph = pick_stage_graph(h->cfg, h->wpb);
+    h->smem_bytes = f64 ? smem_for<double>(h->cfg, h->wpb, h->stage_graph) : smem_for<float>(h->cfg, h->wpb, h->stage_graph);
+    h->fn = f64 ? (const void*)gmpe_step_kernel<double> : (const void*)gmpe_step_kernel<float>;
+  }
+  units = h->num_tiles;
+  const void* fn = h->fn;
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if (h->smem_bytes > (size_t)max_optin) {
@@ -174,7 +204,7 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
   if (per_sm < 1) per_sm = 1;
   // persistent grid: one wave of resident CTAs, tiles strided over it (148 SMs on B200)
   int64_t g = (int64_t)h->sm_count * per_sm;
-  h->grid = (int)(h->num_tiles < g ? h->num_tiles : g);
+  h->grid = (int)(units < g ? units : g);
   cudaSetDevice(prev);
   *out = h;
   return GMPE_OK;
@@ -231,9 +261,9 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   cudaGetDevice(&prev);
   if (prev != h->device) cudaSetDevice(h->device);
   cudaStream_t s = (cudaStream_t)stream;
-  if (c.precision == GMPE_F64) gmpe_step_kernel<double><<<h->grid, h->threads, h->smem_bytes, s>>>(p);
-  else gmpe_step_kernel<float><<<h->grid, h->threads, h->smem_bytes, s>>>(p);
-  cudaError_t e = cudaGetLastError();
+  void* kargs[1] = {(void*)&p};
+  cudaError_t e = cudaLaunchKernel(h->fn, dim3(h->grid), dim3(h->threads), kargs, h->smem_bytes, s);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (prev != h->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e));
   h->launches += 1;

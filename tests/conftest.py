@@ -21,3 +21,21 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_generate_tests(metafunc):
+    """Every GPU test runs twice: with the kernel gmpe_create picks for the configuration
+    (thread-per-world for N = L = 3 worlds, gmpe_small.cuh) and with the tile kernel forced
+    (gmpe_step.cuh), so both mappings stay pinned to the oracle."""
+    if metafunc.definition.get_closest_marker("gpu") is not None:
+        metafunc.fixturenames.append("kernel_variant")
+        metafunc.parametrize("kernel_variant", ["auto", "tile"], indirect=True)
+
+
+@pytest.fixture
+def kernel_variant(request, monkeypatch):
+    if request.param == "tile":
+        monkeypatch.setenv("GMPE_FORCE_TILE", "1")
+    else:
+        monkeypatch.delenv("GMPE_FORCE_TILE", raising=False)
+    return request.param
