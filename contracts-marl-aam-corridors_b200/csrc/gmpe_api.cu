@@ -7,6 +7,7 @@
 #include <new>
 #include <string>
 
+#include "gmpe_coop.cuh"
 #include "gmpe_small.cuh"
 #include "gmpe_step.cuh"
 
@@ -22,7 +23,7 @@ struct gmpe_ctx {
   int grid;
   size_t smem_bytes;
   int stage_graph;
-  int small;  // 1: thread-per-world kernel (gmpe_small.cuh), 0: tile kernel (gmpe_step.cuh)
+  int small;  // KERNEL_TILE (gmpe_step.cuh) / KERNEL_WORLD (gmpe_small.cuh) / KERNEL_COOP (gmpe_coop.cuh)
   const void* fn;
   int64_t launches;
   std::string err;
@@ -96,10 +97,18 @@ static int pick_stage_graph(const GmpeConfig& c, int wpb) {
 }
 
 // Worlds with N = L = 3 and no obstacles / walls (BASELINE configs 1-3) run on the
-// thread-per-world kernel; GMPE_FORCE_TILE=1 keeps them on the tile kernel (A/B tests).
-static bool small_world_kernel(const GmpeConfig& c) {
-  if (const char* t = getenv("GMPE_FORCE_TILE")) if (atoi(t)) return false;
-  return c.num_agents == 3 && c.num_landmarks == 3 && c.num_obstacles == 0 && c.num_walls == 0;
+// lane-per-agent kernel (gmpe_coop.cuh).  GMPE_KERNEL=tile | world | coop overrides the
+// choice (A/B timing, and the tests that keep every mapping pinned to the oracle).
+enum { KERNEL_TILE = 0, KERNEL_WORLD = 1, KERNEL_COOP = 2 };
+static int pick_kernel(const GmpeConfig& c) {
+  const bool small = c.num_agents == 3 && c.num_landmarks == 3 && c.num_obstacles == 0 && c.num_walls == 0;
+  if (!small) return KERNEL_TILE;
+  if (const char* t = getenv("GMPE_FORCE_TILE")) if (atoi(t)) return KERNEL_TILE;
+  if (const char* k = getenv("GMPE_KERNEL")) {
+    if (!strcmp(k, "tile")) return KERNEL_TILE;
+    if (!strcmp(k, "world")) return KERNEL_WORLD;
+  }
+  return KERNEL_COOP;
 }
 
 extern "C" {
@@ -156,9 +165,22 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   const bool f64 = cfg->precision == GMPE_F64;
   const bool july = cfg->scenario == GMPE_SCEN_JULY_TUBE;
-  h->small = small_world_kernel(h->cfg) ? 1 : 0;
+  h->small = pick_kernel(h->cfg);
   int units = 0;  // CTAs needed to cover the batch once
-  if (h->small) {
+  if (h->small == KERNEL_COOP) {
+    // one lane per agent, floor(32 / N) worlds per warp, warps independent: gmpe_coop.cuh
+    h->threads = 32 * GMPE_COOP_WARPS;
+    h->wpb = GMPE_COOP_WARPS * (32 / 3);
+    h->num_tiles = (cfg->num_worlds + h->wpb - 1) / h->wpb;
+    h->stage_graph = 0;
+    if (f64) {
+      h->fn = july ? (const void*)gmpe_step_coop_kernel<double, GMPE_SCEN_JULY_TUBE, 3> : (const void*)gmpe_step_coop_kernel<double, GMPE_SCEN_NAV_GRAPH, 3>;
+      h->smem_bytes = GMPE_COOP_WARPS * (july ? CoopTraits<double, GMPE_SCEN_JULY_TUBE, 3>::SLAB_BYTES : CoopTraits<double, GMPE_SCEN_NAV_GRAPH, 3>::SLAB_BYTES);
+    } else {
+      h->fn = july ? (const void*)gmpe_step_coop_kernel<float, GMPE_SCEN_JULY_TUBE, 3> : (const void*)gmpe_step_coop_kernel<float, GMPE_SCEN_NAV_GRAPH, 3>;
+      h->smem_bytes = GMPE_COOP_WARPS * (july ? CoopTraits<float, GMPE_SCEN_JULY_TUBE, 3>::SLAB_BYTES : CoopTraits<float, GMPE_SCEN_NAV_GRAPH, 3>::SLAB_BYTES);
+    }
+  } else if (h->small == KERNEL_WORLD) {
     // one thread per world, warps are independent: see gmpe_small.cuh
     h->threads = 32 * GMPE_SMALL_WARPS;
     h->wpb = h->threads;

@@ -1,0 +1,635 @@
+// gmpe_coop.cuh -- the GraphMPE step for SMALL worlds (N agents, L == N landmarks, no
+// obstacles / walls, N known at compile time): one LANE per agent, floor(32 / N) worlds
+// per warp.
+//
+// Same contract as gmpe_step_kernel (gmpe_step.cuh): one launch = MultiAgentGraphEnv.step
+// (multiagent/environment.py:1021-1063) for every world of the batch plus graphworker's
+// auto-reset (onpolicy/envs/env_wrappers.py:861-873), or MultiAgentGraphEnv.reset
+// (environment.py:1066-1081) for the masked worlds.
+//
+// Mapping.  State and every per-agent output are [B][N][...] arrays, so "lane = agent" makes
+// a warp's loads and row stores lane-linear: perfectly coalesced with no staging.  The few
+// values an agent needs from the other agents of its world (positions, velocities, status,
+// counters) travel by warp shuffle; nothing but the per-WORLD outputs (adjacency, edge
+// lists) and the observation rows touches shared memory, and the only synchronisation is
+// __syncwarp.  The reference walks the agents in index order with in-place side effects
+// (SURVEY.md H1); lanes reproduce that exactly with the two-pass formulation: what depends
+// on an agent's own state is computed first and exchanged, then agent i reads the
+// post-reward value of agents < i and the pre-reward value of agents > i.
+//
+// Compared with the thread-per-world kernel (gmpe_small.cuh) this gives 3.2x the warps for
+// the same batch and a third of the straight-line code per warp -- that kernel was bound by
+// latency (13.8 warps / SM at 65,536 worlds) and instruction fetch, not by bandwidth.
+#pragma once
+#include "gmpe_small.cuh"
+
+namespace gmpe {
+
+#ifndef GMPE_COOP_WARPS
+#define GMPE_COOP_WARPS 4
+#endif
+#ifndef GMPE_COOP_MINBLOCKS_F32
+#define GMPE_COOP_MINBLOCKS_F32 5
+#endif
+#ifndef GMPE_COOP_MINBLOCKS_F64
+#define GMPE_COOP_MINBLOCKS_F64 2
+#endif
+
+template <typename Real, int SCEN, int N>
+struct CoopTraits {
+  static constexpr int E = 2 * N, EE = E * E, CAP = E * (E - 1);
+  static constexpr int F = SCEN == GMPE_SCEN_JULY_TUBE ? 19 : 6;
+  static constexpr int R = (int)sizeof(Real);
+  static constexpr int WPW = 32 / N;   // worlds per warp
+  static constexpr int AL = WPW * N;   // active lanes
+  static constexpr int up16(int x) { return (x + 15) / 16 * 16; }
+  // staging regions of a warp (bytes); +16: regions are co-aligned with their global span
+  static constexpr int OBS_BYTES = up16(AL * F * R) + 16;
+  static constexpr int ADJ_BYTES = up16(WPW * EE * R) + 16;
+  static constexpr int EIDX_BYTES = up16(WPW * 2 * CAP * 4) + 16;
+  static constexpr int EATTR_BYTES = up16(WPW * CAP * R) + 16;
+  static constexpr int ROUND_A = OBS_BYTES + ADJ_BYTES;
+  static constexpr int ROUND_B = EIDX_BYTES + EATTR_BYTES;
+  static constexpr int SLAB_BYTES = up16(ROUND_A > ROUND_B ? ROUND_A : ROUND_B);
+};
+
+// Contiguous span of n elements: shared -> global with 128-bit vectors.  The span was staged
+// at `slab + ((size_t)g & 15)` so that source and destination are co-aligned; a head / tail
+// shorter than a vector goes out as scalars.  RW = elements per world (for masked launches).
+template <typename T, int RW>
+__device__ __forceinline__ void copy_span(T* __restrict__ g, const unsigned char* __restrict__ region, int n, bool all_worlds,
+                                          uint32_t world_mask, int lane) {
+  const int mis = (int)(reinterpret_cast<size_t>(g) & 15);
+  const T* src = reinterpret_cast<const T*>(region + mis);
+  if (all_worlds) {
+    int head = mis ? (16 - mis) / (int)sizeof(T) : 0;
+    if (head > n) head = n;
+    if (lane < head) g[lane] = src[lane];
+    constexpr int VW = 16 / (int)sizeof(T);
+    const int nv = (n - head) / VW;
+    const int4* s4 = reinterpret_cast<const int4*>(src + head);
+    int4* d4 = reinterpret_cast<int4*>(g + head);
+#pragma unroll 4
+    for (int q = lane; q < nv; q += 32) d4[q] = s4[q];
+    for (int q = head + nv * VW + lane; q < n; q += 32) g[q] = src[q];
+  } else {
+#pragma unroll 1
+    for (int q = lane; q < n; q += 32)
+      if ((world_mask >> (q / RW)) & 1u) g[q] = src[q];
+  }
+}
+
+template <typename Real>
+__device__ __forceinline__ Real shfl_(Real v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+template <typename Real, int SCEN, int N>
+__global__ void __launch_bounds__(32 * GMPE_COOP_WARPS, sizeof(Real) == 4 ? GMPE_COOP_MINBLOCKS_F32 : GMPE_COOP_MINBLOCKS_F64)
+gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
+  using V2 = typename RT<Real>::V2;
+  using V4 = typename RT<Real>::V4;
+  using T = CoopTraits<Real, SCEN, N>;
+  constexpr int E = T::E, EE = T::EE, CAP = T::CAP, F = T::F, WPW = T::WPW, AL = T::AL;
+  constexpr bool july = SCEN == GMPE_SCEN_JULY_TUBE;
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  __shared__ Real acttab[2 * 32];
+
+  const GmpeConfig& c = p.c;
+  const int B = c.num_worlds;
+  const bool heading = c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR;
+  const bool do_info = (c.flags & GMPE_FLAG_INFO) != 0;
+  const bool step_mode = p.mode == MODE_STEP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* slab = smem_raw + (size_t)warp * T::SLAB_BYTES;
+
+  // _set_action table (environment.py:336-475): identical arithmetic to decode_action
+  if (threadIdx.x < 32) {
+    Real u0 = Real(0), u1 = Real(0);
+    if ((int)threadIdx.x < c.total_actions) decode_action<Real>(c, threadIdx.x, u0, u1);
+    acttab[2 * threadIdx.x] = u0;
+    acttab[2 * threadIdx.x + 1] = u1;
+  }
+  __syncthreads();
+
+  Real* g_as = (Real*)p.st.agent_state;
+  Real* g_aux = (Real*)p.st.agent_aux;
+  uint32_t* g_fl = (uint32_t*)p.st.agent_flags;
+  int32_t* g_cnt = p.st.agent_cnt;
+  Real* g_wf = (Real*)p.st.world_f;
+  int32_t* g_wi = p.st.world_i;
+  Real* g_lm = (Real*)p.st.landmarks;
+
+  const Real sep = Real(c.separation_dist), thr_goal = Real(c.goal_dist_thresh);
+  const Real coll = Real(c.collision_rew), goal = Real(c.goal_rew);
+  const Real dt = Real(c.dt);
+  const bool env_e = (c.flags & GMPE_FLAG_ENV_EDGES) && p.out.edge_index;
+  const bool gnn_e = (c.flags & GMPE_FLAG_GNN_EDGES) && p.out.gnn_edge_index;
+
+  // lane -> (world of the warp, agent)
+  const int wl = lane / N;
+  const int i = lane - wl * N;
+  const bool lane_used = lane < AL;
+  const int lb = lane_used ? wl * N : 0;  // first lane of this lane's world (shuffle base)
+
+  const int64_t num_groups = ((int64_t)B + WPW - 1) / WPW;
+  for (int64_t grp = (int64_t)blockIdx.x * GMPE_COOP_WARPS + warp; grp < num_groups; grp += (int64_t)gridDim.x * GMPE_COOP_WARPS) {
+    const int64_t wbase = grp * WPW;
+    const int nwv = (int)min((int64_t)WPW, (int64_t)B - wbase);  // worlds of this warp
+    const bool valid = lane_used && wl < nwv;
+    const int64_t b = wbase + (valid ? wl : 0);                   // idle lanes shadow world wbase, never write
+    const size_t ga = (size_t)b * N + (valid ? i : 0);            // global agent slot (lane-linear)
+
+    // ---------------- loads: one agent per lane, coalesced ------------------------------
+    V4 s = ((const V4*)g_as)[ga];
+    V2 aux = ((const V2*)g_aux)[ga];
+    const uint32_t flw = g_fl[ga];
+    V2 lmi = ((const V2*)g_lm)[ga];  // landmark i == goal of agent i (goal_match_index = arange, july:356)
+    int st_pre = flw & 0xff, pp = (flw >> 8) & 0xff, pr = (flw >> 16) & 0xff, gr = (flw >> 24) & 0xff;
+    Real wf[12];
+    Real dsum0 = Real(0);
+    if (july) {
+      const Real* gw_ = g_wf + (size_t)b * GMPE_WORLD_F;
+#pragma unroll
+      for (int q = 0; q < 12; ++q) wf[q] = gw_[q];
+      if (do_info) dsum0 = gw_[GMPE_WF_DELTA_SPACING];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 12; ++q) wf[q] = Real(0);
+    }
+    const int2 wi = *reinterpret_cast<const int2*>(g_wi + (size_t)b * GMPE_WORLD_I);
+    const int wstep = step_mode ? wi.x + 1 : wi.x;  // environment.py:1024
+    const int wep = wi.y;
+    int32_t cnt[GMPE_AGENT_CNT];
+    if (do_info && step_mode) {
+      const int4 a = ((const int4*)(g_cnt + ga * GMPE_AGENT_CNT))[0];
+      const int4 bq = ((const int4*)(g_cnt + ga * GMPE_AGENT_CNT))[1];
+      cnt[0] = a.x; cnt[1] = a.y; cnt[2] = a.z; cnt[3] = a.w;
+      cnt[4] = bq.x; cnt[5] = bq.y; cnt[6] = bq.z; cnt[7] = bq.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < GMPE_AGENT_CNT; ++q) cnt[q] = 0;
+    }
+
+    V2 vpre = RT<Real>::mk2(0, 0), vpost = vpre;
+    Real hx = Real(1), hy = Real(0);
+    int st_post = st_pre, ph_obs = 0;
+    bool rs = false;  // this world is (re)placed in this launch
+    bool wr = valid;  // this world's tensors are emitted by this launch
+    Real rew = Real(0);
+    int done = 0;
+
+    if (step_mode) {
+      // ---------------- stage 2 + stage 1: action decode and physics --------------------
+      const int a = p.act[ga];
+      const Real u0 = acttab[2 * (a & 31)], u1 = acttab[2 * (a & 31) + 1];
+      if (c.physics == GMPE_PHYS_FORCE) {
+        // classic step order (onpolicy/envs/mpe/core.py:183-202) with the force functions of
+        // multiagent/core.py:766-984, accumulated over the other agents in entity order
+        const bool classic = (c.flags & GMPE_FLAG_CLASSIC_CONTACT) != 0;
+        const Real km = Real(c.contact_margin), cf = Real(c.contact_force);
+        const Real dmin = classic ? Real(c.entity_size) + Real(c.entity_size) : sep;
+        Real fx = u0, fy = u1;  // apply_action_force: mass 1, accel None, no noise
+        const bool feels = classic || !st_pre;  // core.py:899: no agent-agent force on a done entity
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const Real qx = shfl_(s.x, lb + k), qy = shfl_(s.y, lb + k);
+          const bool other = feels && k != i;
+          const Real dx = other ? s.x - qx : Real(0), dy = other ? s.y - qy : Real(0);
+          const Real dist = other ? norm2(dx, dy) : Real(1);
+          const Real pen = softplus(-(dist - dmin) / km) * km;
+          fx = cf * dx / dist * pen + fx;  // the self / unfelt term is exactly +0 * pen
+          fy = cf * dy / dist * pen + fy;
+        }
+        if (feels) {  // integrate_state core.py:827-845; done agents freeze
+          s.z = s.z * Real(1 - c.damping) + fx * dt;
+          s.w = s.w * Real(1 - c.damping) + fy * dt;
+          if (c.max_speed > 0) {
+            const Real speed = sqrt_(s.z * s.z + s.w * s.w);
+            if (speed > Real(c.max_speed)) { s.z = s.z / speed * Real(c.max_speed); s.w = s.w / speed * Real(c.max_speed); }
+          }
+          s.x += s.z * dt; s.y += s.w * dt;
+          aux.x += norm2(s.z * dt, s.w * dt);
+        }
+      } else if (!st_pre) {
+        integrate_kinematic<Real>(c, s, u0, u1, aux.x);  // core.py:819-826
+      }
+    }
+
+    // pre-reward velocity and heading vector (july:1130-1131)
+    if (heading) { sincos_(s.z, &hy, &hx); vpre = RT<Real>::mk2(s.w * hx, s.w * hy); }
+    else {
+      vpre = RT<Real>::mk2(s.z, s.w);
+      const Real sp = norm2(s.z, s.w);  // DoubleIntegratorXYState.theta = arctan2(vy, vx), core.py:188-189
+      if (sp > Real(0)) { hx = s.z / sp; hy = s.w / sp; }
+    }
+    vpost = vpre;
+
+    // positions / goals of the whole world, by shuffle
+    Real PX[N], PY[N], LX[N], LY[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      PX[k] = shfl_(s.x, lb + k); PY[k] = shfl_(s.y, lb + k);
+      LX[k] = shfl_(lmi.x, lb + k); LY[k] = shfl_(lmi.y, lb + k);
+    }
+    // row i of the agent-agent and agent-landmark distances (calculate_distances, core.py:600-624)
+    Real daa[N], dal[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      daa[k] = norm2(PX[k] - s.x, PY[k] - s.y);
+      dal[k] = norm2(s.x - LX[k], s.y - LY[k]);
+    }
+    const Real d_goal = norm2(s.x - lmi.x, s.y - lmi.y);
+
+    Real sp_err = Real(0);
+    int32_t c_old[3] = {cnt[GMPE_AC_DIST_TRAV_I], cnt[GMPE_AC_TIME_REQ_I], cnt[GMPE_AC_SPACING_VIOL]};
+    if (step_mode) {
+      // ---------------- pass A: what reward() derives from the agent's own state -----------
+      int pp_eff = pp, ph = 0;
+      bool reach;
+      if (july) {
+        ph = tube_phase<Real>(wf, s.x, s.y, pp_eff);  // observation-time call may promote pp (july:727)
+        reach = (ph == 2) && (pr != 0) && (d_goal < thr_goal) && !st_pre;
+      } else {
+        reach = (d_goal < thr_goal) && (c.flags & GMPE_FLAG_USE_DONES) && !st_pre;
+      }
+      ph_obs = ph;
+      if (reach) {  // agent.status = True; state.reset_velocity() (july:1188-1190, core.py:324-333)
+        st_post = 1;
+        if (heading) {
+          if (july) {
+            Real th = p.theta ? ((const Real*)p.theta)[ga] : Real(NAN);
+            if (isnan_(th))
+              th = Real(philox_uniform(c.seed, c.world_offset + b, (uint32_t)wep,
+                                       (1u << 30) + (uint32_t)wstep * 64u + (uint32_t)i, 0.0, 6.283185307179586));
+            s.z = wrap_heading(th);
+          }
+          s.w = Real(c.v_min);
+          Real sn, cs;
+          sincos_(s.z, &sn, &cs);
+          vpost = RT<Real>::mk2(s.w * cs, s.w * sn);
+        } else { s.z = Real(0); s.w = Real(0); vpost = RT<Real>::mk2(0, 0); }
+      }
+
+      // ---------------- pass B: terms that look at other agents -----------------
+      int ncoll_rew = 0, ncoll_info = 0;
+      int front = -1, back = -1;
+      Real fproj = Real(0), bproj = Real(0), fdist = Real(0), bdist = Real(0);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const int sq = __shfl_sync(0xffffffffu, st_post, lb + k), sp_ = __shfl_sync(0xffffffffu, st_pre, lb + k);
+        if (k == i) continue;
+        const int st_k = k < i ? sq : sp_;
+        const Real d = daa[k];
+        const bool close = d < sep;
+        ncoll_rew += (close && !st_k && !st_pre);    // is_collision at reward(i) time (july:907-914)
+        ncoll_info += (close && !st_k && !st_post);  // ... at info_callback(i) time (july:785)
+        if (july) {  // front / back neighbours along the own heading (july:1136-1143)
+          const Real rx = PX[k] - s.x, ry = PY[k] - s.y;
+          const Real proj = rx * hx + ry * hy;
+          if (proj > Real(0)) { if (front < 0 || proj < fproj) { front = k; fproj = proj; fdist = d; } }
+          else { if (back < 0 || proj > bproj) { back = k; bproj = proj; bdist = d; } }
+        }
+      }
+      int cur = ph;
+      if (july) {
+        rew -= Real(ncoll_rew) * (coll * Real(4));
+        const Real tdx = wf[GMPE_WF_EXIT_X] - wf[GMPE_WF_ENT_X], tdy = wf[GMPE_WF_EXIT_Y] - wf[GMPE_WF_ENT_Y];
+        const Real tube_length = norm2(tdx, tdy);
+        if (ph == 2 && ph > pp_eff + 1) rew -= goal * Real(3);  // july:1149
+        const Real ex = s.x - wf[GMPE_WF_ENT_X], ey = s.y - wf[GMPE_WF_ENT_Y];
+        const Real proj = ex * (tdx / tube_length) + ey * (tdy / tube_length);
+        const Real edist = norm2(ex - proj * tdx, ey - proj * tdy);  // un-normalised direction, july:1154
+        if (ph == pp_eff + 1 && pr == ph - 1) {                      // july:1156-1160
+          if (ph == 1 && Real(0) <= proj && proj < Real(0.1) * tube_length && edist < Real(0.2) * tube_length) rew += goal * Real(3);
+          else if (ph == 2) rew += goal * Real(3);
+        }
+        if (ph == 0) {
+          rew -= norm2(wf[GMPE_WF_ENT_X] - s.x, wf[GMPE_WF_ENT_Y] - s.y);
+        } else if (ph == 1) {  // metering terms, july:1167-1181
+          if (front >= 0) { const Real diff = fdist - sep; sp_err += diff < Real(0) ? abs_(diff) : Real(0); }
+          if (back >= 0) { const Real diff = bdist - sep; sp_err += diff < Real(0) ? abs_(diff) : Real(0); }
+          if (sp_err > Real(0)) cnt[GMPE_AC_SPACING_VIOL] += 1;
+          rew -= sp_err * Real(c.formation_rew);
+          rew -= norm2(wf[GMPE_WF_EXIT_X] - s.x, wf[GMPE_WF_EXIT_Y] - s.y);
+          cnt[GMPE_AC_STEPS_IN_CORRIDOR] += 1;
+        } else if (ph == 2 && pr == 0) {
+          cur = 0;
+        } else {  // july:1185-1194
+          if (d_goal < thr_goal) { if (reach) rew += goal * Real(5); }
+          else rew -= d_goal;
+        }
+        if (pr == 1 && cur == 0) cnt[GMPE_AC_CONFORMANCE] += 1;
+        if (cur > pr) pr = cur;
+        if (cur < pp_eff) rew -= coll * Real(3);
+        if (cur < pr) rew -= coll;
+        pp = cur;
+        rew = clip(rew, -Real(4) * coll, goal * Real(5));
+        rew = clip(rew, Real(c.min_reward), Real(c.max_reward));
+      } else {
+        rew -= Real(ncoll_rew) * coll;
+        if (d_goal < thr_goal) rew += goal; else rew -= d_goal;
+      }
+      done = (st_post || wstep >= c.episode_length) ? 1 : 0;  // environment.py:264-271
+
+      if (do_info) {  // info_callback own-state part (july:741-787); int32 truncation as the int64 numpy arrays
+        int nearest = 0;
+        Real dmin = dal[0];
+#pragma unroll
+        for (int l = 1; l < N; ++l)
+          if (dal[l] < dmin) { dmin = dal[l]; nearest = l; }
+        int g = gr - 1;
+        const int32_t tnow = (int32_t)((double)wstep * c.dt);
+        const int32_t pd = (int32_t)aux.x, dl = (int32_t)dmin;
+        if (dmin < thr_goal && (nearest != g && g != -1)) { g = nearest; cnt[GMPE_AC_DIST_LEFT_I] = dl; }
+        if (dmin < thr_goal && cnt[GMPE_AC_TIME_REQ_I] == -1) { cnt[GMPE_AC_TIME_REQ_I] = tnow; cnt[GMPE_AC_DIST_TRAV_I] = pd; cnt[GMPE_AC_DIST_LEFT_I] = dl; g = nearest; }
+        if (cnt[GMPE_AC_TIME_REQ_I] == -1) { cnt[GMPE_AC_DIST_TRAV_I] = pd; cnt[GMPE_AC_DIST_LEFT_I] = dl; }
+        if (dmin > thr_goal && cnt[GMPE_AC_TIME_REQ_I] != -1) { cnt[GMPE_AC_DIST_TRAV_I] = pd; cnt[GMPE_AC_TIME_REQ_I] = tnow; cnt[GMPE_AC_DIST_LEFT_I] = dl; }
+        if (dmin < thr_goal && nearest == g) { cnt[GMPE_AC_DIST_LEFT_I] = dl; g = nearest; }
+        gr = g + 1;
+        cnt[GMPE_AC_AGENT_COLL] += ncoll_info;
+      }
+
+      // ---------------- reward / done / info outputs ----------------------------------------
+      // world-level exchanges (all lanes take part; values of idle lanes are never used)
+      Real rsum = Real(0);
+#pragma unroll
+      for (int k = 0; k < N; ++k) rsum += shfl_(rew, lb + k);  // environment.py:1056-1059, agent order
+      const uint32_t dmask = __ballot_sync(0xffffffffu, done != 0);
+      const bool all_done = ((dmask >> lb) & ((1u << N) - 1u)) == ((1u << N) - 1u);
+      Real dsum = dsum0;
+      if (do_info) {
+        // world-level statistics are recomputed inside every agent's info_callback while later
+        // agents still hold last step's values (july:789-793, 800-823)
+        Real dm = Real(0), tm = Real(0), sv = Real(0);
+        Real cd[N], ct[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const int n0 = __shfl_sync(0xffffffffu, cnt[GMPE_AC_DIST_TRAV_I], lb + k), o0 = __shfl_sync(0xffffffffu, c_old[0], lb + k);
+          const int n1 = __shfl_sync(0xffffffffu, cnt[GMPE_AC_TIME_REQ_I], lb + k), o1 = __shfl_sync(0xffffffffu, c_old[1], lb + k);
+          const int n2 = __shfl_sync(0xffffffffu, cnt[GMPE_AC_SPACING_VIOL], lb + k), o2 = __shfl_sync(0xffffffffu, c_old[2], lb + k);
+          const Real spk = shfl_(sp_err, lb + k);
+          const bool nw_ = k <= i;
+          cd[k] = Real(nw_ ? n0 : o0); ct[k] = Real(nw_ ? n1 : o1);
+          dm += cd[k]; tm += ct[k]; sv += Real(nw_ ? n2 : o2);
+          if (nw_) dsum += spk;
+        }
+        dm = qdiv(dm, Real(N)); tm = qdiv(tm, Real(N));
+        Real ds = Real(0), ts = Real(0);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const Real x = cd[k] - dm, y = ct[k] - tm;
+          ds += x * x; ts += y * y;
+        }
+        ds = sqrt_(qdiv(ds, Real(N))); ts = sqrt_(qdiv(ts, Real(N)));
+        if (valid && p.out.info) {
+          Real* gi = (Real*)p.out.info + ga * GMPE_INFO_K;
+          const Real lo[8] = {Real(cnt[GMPE_AC_DIST_LEFT_I]), Real(cnt[GMPE_AC_TIME_REQ_I]), Real(cnt[GMPE_AC_AGENT_COLL]), Real(cnt[GMPE_AC_OBST_COLL]),
+                              dm, ds, qdiv(dm, ds + Real(0.0001)), Real(cnt[GMPE_AC_DIST_TRAV_I])};
+          const Real hi[8] = {Real(cnt[GMPE_AC_TIME_REQ_I]), tm, ts, qdiv(tm, ts + Real(0.0001)),
+                              qdiv(Real(cnt[GMPE_AC_CONFORMANCE]), Real(c.episode_length)),
+                              qdiv(dsum, sv != Real(0) ? sv : Real(1)),
+                              qdiv(Real(cnt[GMPE_AC_SPACING_VIOL]), cnt[GMPE_AC_STEPS_IN_CORRIDOR] != 0 ? Real(cnt[GMPE_AC_STEPS_IN_CORRIDOR]) : Real(1)),
+                              aux.y};
+          store_row8(gi, lo);
+          store_row8(gi + 8, hi);
+        }
+      }
+      if (valid) {
+        const bool collab = (c.flags & GMPE_FLAG_COLLABORATIVE) != 0;
+        ((Real*)p.out.reward)[ga] = collab ? rsum : rew;
+        if (p.out.indiv_reward) ((Real*)p.out.indiv_reward)[ga] = rew;
+        p.out.done[ga] = (uint8_t)done;
+      }
+      rs = valid && (c.flags & GMPE_FLAG_AUTO_RESET) && all_done;
+      if (valid && !rs) {
+        // ---------------- state write-back ---------------------------------------------------
+        ((V4*)g_as)[ga] = s;
+        ((V2*)g_aux)[ga] = aux;
+        g_fl[ga] = (uint32_t)st_post | ((uint32_t)pp << 8) | ((uint32_t)pr << 16) | ((uint32_t)gr << 24);
+        if (i == 0) g_wi[(size_t)b * GMPE_WORLD_I + GMPE_WI_STEP] = wstep;
+        if (july && do_info && i == N - 1) g_wf[(size_t)b * GMPE_WORLD_F + GMPE_WF_DELTA_SPACING] = dsum;
+        if (do_info) {
+          int4* gc = (int4*)(g_cnt + ga * GMPE_AGENT_CNT);
+          gc[0] = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
+          gc[1] = make_int4(cnt[4], cnt[5], cnt[6], cnt[7]);
+        }
+      }
+    } else {
+      const bool m = p.env_mask ? (p.env_mask[b] != 0) : true;
+      rs = valid && m;
+      wr = rs;
+    }
+
+    // ---------------- reset (auto-reset of finished worlds, or MODE_RESET) -------------------
+    // reset_world (july:339-420): counters cleared, previous_phase survives.
+    // Every lane of the world evaluates the same placement and keeps its own agent.
+    const bool any_rs = __any_sync(0xffffffffu, rs);
+    if (rs) {
+      if (p.has_rst) {
+        const Real* rwf = (const Real*)p.rst.world_f + (size_t)b * GMPE_WORLD_F;
+#pragma unroll
+        for (int q = 0; q < 12; ++q) wf[q] = rwf[q];
+        lmi = ((const V2*)p.rst.landmarks)[ga];
+        s = ((const V4*)p.rst.agent_state)[ga];
+        aux.y = ((const V2*)p.rst.agent_aux)[ga].y;
+      } else {
+        const Placed<Real, N> pl = place_small<Real, SCEN, N>(c, c.world_offset + b, (uint32_t)wep);
+        if (july) {
+#pragma unroll
+          for (int q = 0; q < 12; ++q) wf[q] = pl.wf[q];
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          if (k == i) { s = pl.s[k]; lmi = pl.lm[k]; }
+        aux.y = c.max_speed > 0 ? norm2(s.x - lmi.x, s.y - lmi.y) / Real(c.max_speed) : Real(INFINITY);  // min_time july:941-951
+      }
+      // persist the world-level arrays
+      if (i == 0) {
+        Real* gw_ = g_wf + (size_t)b * GMPE_WORLD_F;
+        if (july || p.has_rst) {
+#pragma unroll
+          for (int q = 0; q < 12; ++q) gw_[q] = wf[q];
+        }
+        gw_[GMPE_WF_DELTA_SPACING] = Real(0);
+        g_wi[(size_t)b * GMPE_WORLD_I + GMPE_WI_STEP] = 0;
+        g_wi[(size_t)b * GMPE_WORLD_I + GMPE_WI_EPISODE] = wep + 1;
+      }
+      ((V2*)g_lm)[ga] = lmi;
+      aux.x = Real(0);
+      st_post = 0;
+      if (heading) { Real sn, cs; sincos_(s.z, &sn, &cs); vpre = RT<Real>::mk2(s.w * cs, s.w * sn); }
+      else vpre = RT<Real>::mk2(s.z, s.w);
+      vpost = vpre;
+      // observations of the fresh episode replace the terminal ones (env_wrappers.py:867-873)
+      ph_obs = july ? tube_phase<Real>(wf, s.x, s.y, pp) : 0;
+      ((V4*)g_as)[ga] = s;
+      ((V2*)g_aux)[ga] = aux;
+      g_fl[ga] = (uint32_t)0 | ((uint32_t)pp << 8);
+      if (do_info || !step_mode) {
+        int4* gc = (int4*)(g_cnt + ga * GMPE_AGENT_CNT);
+        gc[0] = make_int4(0, 0, 0, 0);
+        gc[1] = make_int4(0, -1, -1, -1);
+      }
+    }
+    if (any_rs) {  // refresh the exchanged positions / goals and the own distance rows
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        PX[k] = shfl_(s.x, lb + k); PY[k] = shfl_(s.y, lb + k);
+        LX[k] = shfl_(lmi.x, lb + k); LY[k] = shfl_(lmi.y, lb + k);
+      }
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        daa[k] = norm2(PX[k] - s.x, PY[k] - s.y);
+        dal[k] = norm2(s.x - LX[k], s.y - LY[k]);
+      }
+    }
+    const uint32_t lane_wr = __ballot_sync(0xffffffffu, wr);
+    if (lane_wr == 0) continue;
+    // world-level write mask (bit w = world w of this warp) and "every world of the warp"
+    uint32_t wmask = 0;
+#pragma unroll
+    for (int w = 0; w < WPW; ++w) wmask |= ((lane_wr >> (w * N)) & 1u) << w;
+    const bool all_worlds = wmask == ((nwv == 32 ? 0u : (1u << nwv)) - 1u);
+
+    // velocities / final status of the whole world
+    Real VPX[N], VPY[N], VQX[N], VQY[N];
+    int STF[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      VPX[k] = shfl_(vpre.x, lb + k); VPY[k] = shfl_(vpre.y, lb + k);
+      VQX[k] = shfl_(vpost.x, lb + k); VQY[k] = shfl_(vpost.y, lb + k);
+      STF[k] = __shfl_sync(0xffffffffu, st_post, lb + k);
+    }
+
+    // ---------------- emission: node features of ego = this lane's agent ---------------------
+    // _get_entity_feat_relative (july:1694-1771): [rel_vel, rel_pos, rel_goal, occupied, type];
+    // ego i sees agents <= i with their post-reward velocity, agents > i pre-reward
+    if (p.out.node_obs && wr) {
+      Real* g_node = (Real*)p.out.node_obs + ga * (size_t)(E * 8);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const bool post = k <= i;
+        const Real vkx = post ? VQX[k] : VPX[k], vky = post ? VQY[k] : VPY[k];
+        const Real f[8] = {vkx - vpost.x, vky - vpost.y, PX[k] - s.x, PY[k] - s.y,
+                           LX[k] - s.x, LY[k] - s.y, Real(0), Real(0)};  // landmark_poses[entity.id] (july:1740)
+        store_row8(g_node + k * 8, f);
+      }
+#pragma unroll
+      for (int l = 0; l < N; ++l) {
+        const Real rx = LX[l] - s.x, ry = LY[l] - s.y;
+        const Real f[8] = {Real(0) - vpost.x, Real(0) - vpost.y, rx, ry, rx, ry, Real(1), Real(1)};
+        store_row8(g_node + (N + l) * 8, f);
+      }
+    }
+
+    // ---------------- emission: obs rows + adjacency (staged, round A) -------------------------
+    Real* g_obs = p.out.obs ? (Real*)p.out.obs + (size_t)wbase * N * F : nullptr;
+    Real* g_adj = p.out.adj ? (Real*)p.out.adj + (size_t)wbase * EE : nullptr;
+    unsigned char* obs_region = slab;
+    unsigned char* adj_region = slab + T::OBS_BYTES;
+    Real* obs_s = reinterpret_cast<Real*>(obs_region + (reinterpret_cast<size_t>(g_obs) & 15)) + lane * F;
+    Real* adj_s = reinterpret_cast<Real*>(adj_region + (reinterpret_cast<size_t>(g_adj) & 15)) + wl * EE;
+    // rows i and N + i of the masked distance matrix (july:1625-1648): done agents and the
+    // landmark a done agent reached (goal_tracker[l] == l) are disconnected
+    Real row_a[E], row_l[E];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const bool dead = st_post || STF[k];
+      // agent i -> agent k, agent i -> landmark k
+      row_a[k] = (k == i || dead) ? Real(0) : daa[k];
+      row_a[N + k] = dead ? Real(0) : dal[k];
+      // landmark i -> agent k, landmark i -> landmark k
+      row_l[k] = dead ? Real(0) : norm2(lmi.x - PX[k], lmi.y - PY[k]);
+      row_l[N + k] = (k == i || dead) ? Real(0) : norm2(lmi.x - LX[k], lmi.y - LY[k]);
+    }
+    if (lane_used) {
+      if (july) {  // Scenario.observation (july:1337-1463)
+        Real d1 = Real(0), d2 = Real(0);
+        V2 r1 = RT<Real>::mk2(0, 0), r2 = RT<Real>::mk2(0, 0);
+        int seen = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {  // two nearest others, stable on ties (july:1399-1415)
+          if (k == i) continue;
+          const Real rx = PX[k] - s.x, ry = PY[k] - s.y, d = daa[k];
+          if (seen == 0 || d < d1) { d2 = d1; r2 = r1; d1 = d; r1 = RT<Real>::mk2(rx, ry); }
+          else if (seen == 1 || d < d2) { d2 = d; r2 = RT<Real>::mk2(rx, ry); }
+          ++seen;
+        }
+        const Real gx = lmi.x - s.x, gy = lmi.y - s.y;
+        Real* o = obs_s;
+        o[0] = s.x; o[1] = s.y; o[2] = vpre.x; o[3] = vpre.y;
+        o[4] = gx; o[5] = gy; o[6] = Real(0); o[7] = gx; o[8] = gy;
+        o[9] = r1.x; o[10] = r1.y; o[11] = r2.x; o[12] = r2.y;
+        o[13] = wf[GMPE_WF_ENT_X] - s.x; o[14] = wf[GMPE_WF_ENT_Y] - s.y;
+        o[15] = wf[GMPE_WF_EXIT_X] - s.x; o[16] = wf[GMPE_WF_EXIT_Y] - s.y;
+        o[17] = wf[GMPE_WF_WIDTH];
+        o[18] = Real(ph_obs);
+      } else {
+        Real* o = obs_s;
+        o[0] = vpre.x; o[1] = vpre.y; o[2] = s.x; o[3] = s.y; o[4] = lmi.x - s.x; o[5] = lmi.y - s.y;
+      }
+#pragma unroll
+      for (int q = 0; q < E; ++q) { adj_s[i * E + q] = row_a[q]; adj_s[(N + i) * E + q] = row_l[q]; }
+    }
+    __syncwarp();
+    if (g_obs) copy_span<Real, N * F>(g_obs, obs_region, nwv * N * F, all_worlds, wmask, lane);
+    if (g_adj) copy_span<Real, EE>(g_adj, adj_region, nwv * EE, all_worlds, wmask, lane);
+    __syncwarp();
+
+    // ---------------- emission: edge lists (staged, round B, once per list) ---------------------
+    // update_graph (july:1651-1670): (d <= max_edge_dist) & (d > 0), row-major COO;
+    // process_adj (gnn_new.py:328-358) on the fp32 cast: strict <.  A lane compacts rows i and
+    // N + i; the row offsets come from a shuffle prefix over the world's row counts.
+    const Real thr_env = Real(c.coordination_range);
+    const float thr_gnn = (float)c.gnn_max_edge_dist;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      if (!(pass == 0 ? env_e : gnn_e)) continue;
+      int32_t* g_ei = (pass == 0 ? p.out.edge_index : p.out.gnn_edge_index) + (size_t)wbase * 2 * CAP;
+      Real* g_ea = (Real*)(pass == 0 ? p.out.edge_attr : p.out.gnn_edge_attr) + (size_t)wbase * CAP;
+      int32_t* g_ne = pass == 0 ? p.out.num_edges : p.out.gnn_num_edges;
+      unsigned char* ei_region = slab;
+      unsigned char* ea_region = slab + T::EIDX_BYTES;
+      int32_t* ei_w = reinterpret_cast<int32_t*>(ei_region + (reinterpret_cast<size_t>(g_ei) & 15));
+      Real* ea_w = reinterpret_cast<Real*>(ea_region + (reinterpret_cast<size_t>(g_ea) & 15));
+      // -1 / 0 padding of the fixed-capacity buffers
+      for (int q = lane; q < WPW * 2 * CAP; q += 32) ei_w[q] = -1;
+      for (int q = lane; q < WPW * CAP; q += 32) ea_w[q] = Real(0);
+      uint32_t on_a = 0, on_l = 0;
+#pragma unroll
+      for (int q = 0; q < E; ++q) {
+        bool a_on, l_on;
+        if (pass == 0) { a_on = row_a[q] > Real(0) && row_a[q] <= thr_env; l_on = row_l[q] > Real(0) && row_l[q] <= thr_env; }
+        else { const float fa = (float)row_a[q], fl_ = (float)row_l[q]; a_on = fa > 0.0f && fa < thr_gnn; l_on = fl_ > 0.0f && fl_ < thr_gnn; }
+        on_a |= (uint32_t)a_on << q;
+        on_l |= (uint32_t)l_on << q;
+      }
+      const int ca = __popc(on_a), cl = __popc(on_l);
+      int off_a = 0, off_l = 0, n_edges = 0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const int cak = __shfl_sync(0xffffffffu, ca, lb + k), clk = __shfl_sync(0xffffffffu, cl, lb + k);
+        if (k < i) { off_a += cak; off_l += clk; }
+        off_l += cak;  // landmark rows follow all agent rows
+        n_edges += cak + clk;
+      }
+      __syncwarp();
+      if (lane_used) {
+        int32_t* ei = ei_w + wl * 2 * CAP;
+        Real* ea = ea_w + wl * CAP;
+        int na = off_a, nl = off_l;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+          if ((on_a >> q) & 1u) { ei[na] = i; ei[CAP + na] = q; ea[na] = pass == 0 ? row_a[q] : Real((float)row_a[q]); ++na; }
+          if ((on_l >> q) & 1u) { ei[nl] = N + i; ei[CAP + nl] = q; ea[nl] = pass == 0 ? row_l[q] : Real((float)row_l[q]); ++nl; }
+        }
+      }
+      __syncwarp();
+      copy_span<int32_t, 2 * CAP>(g_ei, ei_region, nwv * 2 * CAP, all_worlds, wmask, lane);
+      copy_span<Real, CAP>(g_ea, ea_region, nwv * CAP, all_worlds, wmask, lane);
+      if (wr && i == 0) g_ne[b] = n_edges;
+      __syncwarp();
+    }
+  }
+}
+
+}  // namespace gmpe

@@ -61,7 +61,10 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, int64_t world, u
 
 // ---- scalar math --------------------------------------------------------------------
 __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
-__device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+// sqrtf / the fp32 quotient branch to a ~35-instruction slow path when an operand is zero or
+// denormal (FCHK); zeros are common here (coincident landmarks, agents at rest, counters
+// that have not moved), so they are answered up front.  Results are unchanged.
+__device__ __forceinline__ float sqrt_(float x) { return x == 0.0f ? x : sqrtf(x); }
 __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
 __device__ __forceinline__ double abs_(double x) { return fabs(x); }
@@ -75,6 +78,10 @@ __device__ __forceinline__ float log1p_(float x) { return log1pf(x); }
 __device__ __forceinline__ double log1p_(double x) { return log1p(x); }
 __device__ __forceinline__ bool isnan_(float x) { return isnan(x); }
 __device__ __forceinline__ bool isnan_(double x) { return isnan(x); }
+
+// a / b for finite b > 0 (see sqrt_)
+__device__ __forceinline__ float qdiv(float a, float b) { return a == 0.0f ? a : a / b; }
+__device__ __forceinline__ double qdiv(double a, double b) { return a / b; }
 
 // np.linalg.norm of a 2-vector; one definition for every distance so that adjacency,
 // edges and collision tests see identical values.

@@ -60,6 +60,10 @@ struct SmallTraits {
 #ifndef GMPE_SMALL_MINBLOCKS_F64
 #define GMPE_SMALL_MINBLOCKS_F64 3
 #endif
+// 1: node_obs / info rows leave the lane directly as 256-bit stores; 0: staged through the slab
+#ifndef GMPE_SMALL_DIRECT_ROWS
+#define GMPE_SMALL_DIRECT_ROWS 1
+#endif
 
 // ---- warp-cooperative slab -> global copies ------------------------------------------
 // Rows of RW Reals per world, staged at `STRIDE` Reals per lane; world w's row goes to
@@ -70,16 +74,23 @@ __device__ __forceinline__ void copy_rows(Real* __restrict__ g, size_t gstride, 
   constexpr int VW = 16 / (int)sizeof(Real);
   constexpr int VPW = RW / VW;
   static_assert(RW % VW == 0, "row must be a whole number of 128-bit vectors");
-  const int total = nw * VPW;
+  if (nw == 32 && wmask == 0xffffffffu) {  // the hot case: a full warp of worlds, nothing masked
 #pragma unroll
-  for (int it = 0; it < VPW; ++it) {
-    const int q = it * 32 + lane;
-    if (q < total) {
+    for (int it = 0; it < VPW; ++it) {
+      const int q = it * 32 + lane;
       const int w = q / VPW, r = q - w * VPW;
-      if ((wmask >> w) & 1u) {
-        const int4 v = *reinterpret_cast<const int4*>(slab + w * STRIDE + r * VW);
-        *reinterpret_cast<int4*>(g + (size_t)w * gstride + r * VW) = v;
-      }
+      const int4 v = *reinterpret_cast<const int4*>(slab + w * STRIDE + r * VW);
+      *reinterpret_cast<int4*>(g + (size_t)w * gstride + r * VW) = v;
+    }
+    return;
+  }
+  const int total = nw * VPW;
+#pragma unroll 1
+  for (int q = lane; q < total; q += 32) {
+    const int w = q / VPW, r = q - w * VPW;
+    if ((wmask >> w) & 1u) {
+      const int4 v = *reinterpret_cast<const int4*>(slab + w * STRIDE + r * VW);
+      *reinterpret_cast<int4*>(g + (size_t)w * gstride + r * VW) = v;
     }
   }
 }
@@ -92,20 +103,39 @@ __device__ __forceinline__ void copy_flat(T* __restrict__ g, const T* __restrict
   constexpr int VW = 16 / (int)sizeof(T);
   const int n = nw * RW;
   if (wmask == wfull && ((reinterpret_cast<size_t>(g) & 15) == 0)) {
-    const int nv = n / VW;
-    constexpr int ITERS = (32 * RW / VW + 31) / 32;
+    constexpr int NV32 = 32 * RW / VW;  // 32 * RW * sizeof(T) is a multiple of 128
+    if (nw == 32) {
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const int q = it * 32 + lane;
-      if (q < nv) reinterpret_cast<int4*>(g)[q] = reinterpret_cast<const int4*>(slab)[q];
+      for (int it = 0; it < (NV32 + 31) / 32; ++it) {
+        const int q = it * 32 + lane;
+        if (NV32 % 32 == 0 || q < NV32) reinterpret_cast<int4*>(g)[q] = reinterpret_cast<const int4*>(slab)[q];
+      }
+    } else {
+      const int nv = n / VW;
+#pragma unroll 1
+      for (int q = lane; q < nv; q += 32) reinterpret_cast<int4*>(g)[q] = reinterpret_cast<const int4*>(slab)[q];
+      for (int q = nv * VW + lane; q < n; q += 32) g[q] = slab[q];
     }
-    for (int q = nv * VW + lane; q < n; q += 32) g[q] = slab[q];
   } else {  // masked reset launches / unaligned caller buffers
+#pragma unroll 1
     for (int q = lane; q < n; q += 32) {
       const int w = q / RW;
       if ((wmask >> w) & 1u) g[q] = slab[q];
     }
   }
+}
+
+// One feature row of 8 Reals with 256-bit stores (sm_100: STG.E.ENL2.256): a lane writes
+// whole 32-byte sectors, so per-world rows need no staging to reach the memory system as
+// full-sector writes.  p must be 32-byte aligned.
+__device__ __forceinline__ void store_row8(float* p, const float (&f)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]),
+               "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])
+               : "memory");
+}
+__device__ __forceinline__ void store_row8(double* p, const double (&f)[8]) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(f[0]), "d"(f[1]), "d"(f[2]), "d"(f[3]) : "memory");
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + 4), "d"(f[4]), "d"(f[5]), "d"(f[6]), "d"(f[7]) : "memory");
 }
 
 // ---- placement of one world in registers ---------------------------------------------
@@ -524,22 +554,35 @@ gmpe_step_small_kernel(const __grid_constant__ KParams p) {
           for (int k = 0; k < N; ++k) {
             dm += Real(cnt[k][GMPE_AC_DIST_TRAV_I]); tm += Real(cnt[k][GMPE_AC_TIME_REQ_I]); sv += Real(cnt[k][GMPE_AC_SPACING_VIOL]);
           }
-          dm /= Real(N); tm /= Real(N);
+          dm = qdiv(dm, Real(N)); tm = qdiv(tm, Real(N));
           Real ds = Real(0), ts = Real(0);
 #pragma unroll
           for (int k = 0; k < N; ++k) {
             const Real x = Real(cnt[k][GMPE_AC_DIST_TRAV_I]) - dm, y = Real(cnt[k][GMPE_AC_TIME_REQ_I]) - tm;
             ds += x * x; ts += y * y;
           }
-          ds = sqrt_(ds / Real(N)); ts = sqrt_(ts / Real(N));
-          V4* i4 = reinterpret_cast<V4*>(info_s + i * GMPE_INFO_K);
-          i4[0] = RT<Real>::mk4(Real(cc[GMPE_AC_DIST_LEFT_I]), Real(cc[GMPE_AC_TIME_REQ_I]), Real(cc[GMPE_AC_AGENT_COLL]), Real(cc[GMPE_AC_OBST_COLL]));
-          i4[1] = RT<Real>::mk4(dm, ds, dm / (ds + Real(0.0001)), Real(cc[GMPE_AC_DIST_TRAV_I]));
-          i4[2] = RT<Real>::mk4(Real(cc[GMPE_AC_TIME_REQ_I]), tm, ts, tm / (ts + Real(0.0001)));
-          i4[3] = RT<Real>::mk4(Real(cc[GMPE_AC_CONFORMANCE]) / Real(c.episode_length),
-                                dsum / (sv != Real(0) ? sv : Real(1)),
-                                Real(cc[GMPE_AC_SPACING_VIOL]) / (cc[GMPE_AC_STEPS_IN_CORRIDOR] != 0 ? Real(cc[GMPE_AC_STEPS_IN_CORRIDOR]) : Real(1)),
-                                aux[i].y);
+          ds = sqrt_(qdiv(ds, Real(N))); ts = sqrt_(qdiv(ts, Real(N)));
+          const Real iv[GMPE_INFO_K] = {
+              Real(cc[GMPE_AC_DIST_LEFT_I]), Real(cc[GMPE_AC_TIME_REQ_I]), Real(cc[GMPE_AC_AGENT_COLL]), Real(cc[GMPE_AC_OBST_COLL]),
+              dm, ds, qdiv(dm, ds + Real(0.0001)), Real(cc[GMPE_AC_DIST_TRAV_I]),
+              Real(cc[GMPE_AC_TIME_REQ_I]), tm, ts, qdiv(tm, ts + Real(0.0001)),
+              qdiv(Real(cc[GMPE_AC_CONFORMANCE]), Real(c.episode_length)),
+              qdiv(dsum, sv != Real(0) ? sv : Real(1)),
+              qdiv(Real(cc[GMPE_AC_SPACING_VIOL]), cc[GMPE_AC_STEPS_IN_CORRIDOR] != 0 ? Real(cc[GMPE_AC_STEPS_IN_CORRIDOR]) : Real(1)),
+              aux[i].y};
+          if (GMPE_SMALL_DIRECT_ROWS) {
+            if (valid && p.out.info) {
+              Real* gi = (Real*)p.out.info + (ga0 + i) * GMPE_INFO_K;
+              const Real lo[8] = {iv[0], iv[1], iv[2], iv[3], iv[4], iv[5], iv[6], iv[7]};
+              const Real hi[8] = {iv[8], iv[9], iv[10], iv[11], iv[12], iv[13], iv[14], iv[15]};
+              store_row8(gi, lo);
+              store_row8(gi + 8, hi);
+            }
+          } else {
+            V4* i4 = reinterpret_cast<V4*>(info_s + i * GMPE_INFO_K);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) i4[q] = RT<Real>::mk4(iv[4 * q], iv[4 * q + 1], iv[4 * q + 2], iv[4 * q + 3]);
+          }
         }
       }
 
@@ -557,7 +600,7 @@ gmpe_step_small_kernel(const __grid_constant__ KParams p) {
           p.out.done[ga0 + i] = (uint8_t)done[i];
         }
       }
-      if (do_info) {
+      if (do_info && !GMPE_SMALL_DIRECT_ROWS) {
         __syncwarp();
         if (p.out.info)
           copy_rows<Real, T::INFO_RW, T::INFO_STRIDE>((Real*)p.out.info + (size_t)wbase * T::INFO_RW, T::INFO_RW, slab_r, nw, wfull, lane);
@@ -739,10 +782,11 @@ gmpe_step_small_kernel(const __grid_constant__ KParams p) {
         int32_t* ei = reinterpret_cast<int32_t*>(slab) + (size_t)lane * 2 * CAP;
         Real* ea_base = reinterpret_cast<Real*>(slab + (size_t)32 * 2 * CAP * 4);
         Real* ea = ea_base + (size_t)lane * CAP;
+        // -1 / 0 padding of the fixed-capacity buffers (CAP is even: 8-byte vectors always fit)
 #pragma unroll
-        for (int q = 0; q < 2 * CAP; ++q) ei[q] = -1;
+        for (int q = 0; q < CAP; ++q) reinterpret_cast<int2*>(ei)[q] = make_int2(-1, -1);
 #pragma unroll
-        for (int q = 0; q < CAP; ++q) ea[q] = Real(0);
+        for (int q = 0; q < CAP / 2; ++q) reinterpret_cast<V2*>(ea)[q] = RT<Real>::mk2(0, 0);
         int n = 0;
 #pragma unroll
         for (int r = 0; r < E; ++r)
@@ -789,13 +833,19 @@ gmpe_step_small_kernel(const __grid_constant__ KParams p) {
             f[0] = Real(0) - ve.x; f[1] = Real(0) - ve.y; f[2] = q.x - ex; f[3] = q.y - ey;
             f[4] = f[2]; f[5] = f[3]; f[6] = Real(1); f[7] = Real(1);
           }
-          V4* d4 = reinterpret_cast<V4*>(node_s + k * 8);
-          d4[0] = RT<Real>::mk4(f[0], f[1], f[2], f[3]);
-          d4[1] = RT<Real>::mk4(f[4], f[5], f[6], f[7]);
+          if (GMPE_SMALL_DIRECT_ROWS) {
+            if (wr) store_row8(g_node + ((size_t)lane * N + j) * T::NODE_RW + k * 8, f);
+          } else {
+            V4* d4 = reinterpret_cast<V4*>(node_s + k * 8);
+            d4[0] = RT<Real>::mk4(f[0], f[1], f[2], f[3]);
+            d4[1] = RT<Real>::mk4(f[4], f[5], f[6], f[7]);
+          }
         }
-        __syncwarp();
-        copy_rows<Real, T::NODE_RW, T::NODE_STRIDE>(g_node + (size_t)j * T::NODE_RW, (size_t)N * T::NODE_RW, slab_r, nw, wmask, lane);
-        __syncwarp();
+        if (!GMPE_SMALL_DIRECT_ROWS) {
+          __syncwarp();
+          copy_rows<Real, T::NODE_RW, T::NODE_STRIDE>(g_node + (size_t)j * T::NODE_RW, (size_t)N * T::NODE_RW, slab_r, nw, wmask, lane);
+          __syncwarp();
+        }
       }
     }
   }

@@ -739,23 +739,23 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           dm += Real(cc[0]); tm += Real(cc[1]); sv += Real(cc[2]);
           if (k <= (int)i) dsum += sm.sperr[lw * N + k];
         }
-        dm /= Real(N); tm /= Real(N);
+        dm = qdiv(dm, Real(N)); tm = qdiv(tm, Real(N));
         Real ds = Real(0), ts = Real(0);
         for (int k = 0; k < N; ++k) {
           const int32_t* cc = (k <= (int)i ? sm.cnew : sm.cold) + (lw * N + k) * 3;
           Real x = Real(cc[0]) - dm, y = Real(cc[1]) - tm;
           ds += x * x; ts += y * y;
         }
-        ds = sqrt_(ds / Real(N)); ts = sqrt_(ts / Real(N));
+        ds = sqrt_(qdiv(ds, Real(N))); ts = sqrt_(qdiv(ts, Real(N)));
         if (p.out.info) {
           Real* info = (Real*)p.out.info + ga * GMPE_INFO_K;
           V4* i4 = (V4*)info;
           i4[0] = RT<Real>::mk4(Real(cnt[GMPE_AC_DIST_LEFT_I]), Real(cnt[GMPE_AC_TIME_REQ_I]), Real(cnt[GMPE_AC_AGENT_COLL]), Real(cnt[GMPE_AC_OBST_COLL]));
-          i4[1] = RT<Real>::mk4(dm, ds, dm / (ds + Real(0.0001)), Real(cnt[GMPE_AC_DIST_TRAV_I]));
-          i4[2] = RT<Real>::mk4(Real(cnt[GMPE_AC_TIME_REQ_I]), tm, ts, tm / (ts + Real(0.0001)));
-          i4[3] = RT<Real>::mk4(Real(cnt[GMPE_AC_CONFORMANCE]) / Real(c.episode_length),
-                                dsum / (sv != Real(0) ? sv : Real(1)),
-                                Real(cnt[GMPE_AC_SPACING_VIOL]) / (cnt[GMPE_AC_STEPS_IN_CORRIDOR] != 0 ? Real(cnt[GMPE_AC_STEPS_IN_CORRIDOR]) : Real(1)),
+          i4[1] = RT<Real>::mk4(dm, ds, qdiv(dm, ds + Real(0.0001)), Real(cnt[GMPE_AC_DIST_TRAV_I]));
+          i4[2] = RT<Real>::mk4(Real(cnt[GMPE_AC_TIME_REQ_I]), tm, ts, qdiv(tm, ts + Real(0.0001)));
+          i4[3] = RT<Real>::mk4(qdiv(Real(cnt[GMPE_AC_CONFORMANCE]), Real(c.episode_length)),
+                                qdiv(dsum, sv != Real(0) ? sv : Real(1)),
+                                qdiv(Real(cnt[GMPE_AC_SPACING_VIOL]), cnt[GMPE_AC_STEPS_IN_CORRIDOR] != 0 ? Real(cnt[GMPE_AC_STEPS_IN_CORRIDOR]) : Real(1)),
                                 aux.y);
         }
         if (i == (uint32_t)(N - 1)) g_wf[(size_t)b * GMPE_WORLD_F + GMPE_WF_DELTA_SPACING] = dsum;

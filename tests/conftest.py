@@ -24,18 +24,20 @@ def pytest_collection_modifyitems(config, items):
 
 
 def pytest_generate_tests(metafunc):
-    """Every GPU test runs twice: with the kernel gmpe_create picks for the configuration
-    (thread-per-world for N = L = 3 worlds, gmpe_small.cuh) and with the tile kernel forced
-    (gmpe_step.cuh), so both mappings stay pinned to the oracle."""
+    """Every GPU test runs once per kernel mapping: the one gmpe_create picks for the
+    configuration ("auto": lane-per-agent gmpe_coop.cuh for N = L = 3 worlds, the tile kernel
+    gmpe_step.cuh otherwise), the thread-per-world kernel (gmpe_small.cuh) and the tile kernel
+    forced, so every mapping stays pinned to the oracle."""
     if metafunc.definition.get_closest_marker("gpu") is not None:
         metafunc.fixturenames.append("kernel_variant")
-        metafunc.parametrize("kernel_variant", ["auto", "tile"], indirect=True)
+        metafunc.parametrize("kernel_variant", ["auto", "world", "tile"], indirect=True)
 
 
 @pytest.fixture
 def kernel_variant(request, monkeypatch):
-    if request.param == "tile":
-        monkeypatch.setenv("GMPE_FORCE_TILE", "1")
+    monkeypatch.delenv("GMPE_FORCE_TILE", raising=False)
+    if request.param == "auto":
+        monkeypatch.delenv("GMPE_KERNEL", raising=False)
     else:
-        monkeypatch.delenv("GMPE_FORCE_TILE", raising=False)
+        monkeypatch.setenv("GMPE_KERNEL", request.param)
     return request.param

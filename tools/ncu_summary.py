@@ -16,12 +16,19 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
         "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum"]
-MARKS = [("tile loads", "cooperative, coalesced loads"), ("phaseA load/integrate", "phase A: thread = (world, agent)"),
+MARKS_TILE = [("tile loads", "cooperative, coalesced loads"), ("phaseA load/integrate", "phase A: thread = (world, agent)"),
          ("passA", "pass A: everything reward()"), ("passB", "pass B: terms that look"),
          ("outputs/writeback", "reward / done / info outputs"), ("reset", "reset (auto-reset of finished"),
          ("mask+obs copy", "phase B: element-parallel"), ("node_obs", "node_obs: [lw][j][k][8]"),
          ("staged adj/edges", "small worlds: the masked distance"), ("direct adj/edges", "large worlds (or reset-only"),
          ("end", "argmax over the one-hot")]
+MARKS_SMALL = [("copy helpers", "warp-cooperative slab -> global copies"), ("place_small", "placement of one world in registers"),
+               ("prologue/acttab", "the kernel ------"), ("loads", "loads: the whole world into registers"),
+               ("physics", "stage 2 + stage 1: action decode"), ("headings", "pre-reward velocities and heading"),
+               ("distances", "all pairwise distances of the world"), ("agent loop (reward/info)", "stages 3 + 4: agents in index order"),
+               ("reward/done/info out", "reward / done / info outputs"), ("state write-back", "state write-back ----"),
+               ("reset", "reset (auto-reset of finished worlds, or MODE_RESET)"), ("obs+adj", "emission: obs + adj"),
+               ("edges", "emission: edge lists"), ("node_obs", "emission: node features")]
 
 
 def run(args):
@@ -42,7 +49,7 @@ def main(rep, src_path):
                                             "--launch-count", "1"]))))
     src = open(src_path).read().split("\n")
     marks = []
-    for name, needle in MARKS:
+    for name, needle in (MARKS_SMALL if 'small' in src_path else MARKS_TILE):
         for i, l in enumerate(src):
             if needle in l:
                 marks.append((name, i + 1))
