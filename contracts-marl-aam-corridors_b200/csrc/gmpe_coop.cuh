@@ -195,16 +195,16 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
           const bool other = feels && k != i;
           const Real dx = other ? s.x - qx : Real(0), dy = other ? s.y - qy : Real(0);
           const Real dist = other ? norm2(dx, dy) : Real(1);
-          const Real pen = softplus(-(dist - dmin) / km) * km;
-          fx = cf * dx / dist * pen + fx;  // the self / unfelt term is exactly +0 * pen
-          fy = cf * dy / dist * pen + fy;
+          const Real pen = softplus(div_(-(dist - dmin), km)) * km;
+          fx = div_(cf * dx, dist) * pen + fx;  // the self / unfelt term is exactly +0 * pen
+          fy = div_(cf * dy, dist) * pen + fy;
         }
         if (feels) {  // integrate_state core.py:827-845; done agents freeze
           s.z = s.z * Real(1 - c.damping) + fx * dt;
           s.w = s.w * Real(1 - c.damping) + fy * dt;
           if (c.max_speed > 0) {
             const Real speed = sqrt_(s.z * s.z + s.w * s.w);
-            if (speed > Real(c.max_speed)) { s.z = s.z / speed * Real(c.max_speed); s.w = s.w / speed * Real(c.max_speed); }
+            if (speed > Real(c.max_speed)) { s.z = div_(s.z, speed) * Real(c.max_speed); s.w = div_(s.w, speed) * Real(c.max_speed); }
           }
           s.x += s.z * dt; s.y += s.w * dt;
           aux.x += norm2(s.z * dt, s.w * dt);
@@ -219,7 +219,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     else {
       vpre = RT<Real>::mk2(s.z, s.w);
       const Real sp = norm2(s.z, s.w);  // DoubleIntegratorXYState.theta = arctan2(vy, vx), core.py:188-189
-      if (sp > Real(0)) { hx = s.z / sp; hy = s.w / sp; }
+      if (sp > Real(0)) { hx = div_(s.z, sp); hy = div_(s.w, sp); }
     }
     vpost = vpre;
 
@@ -296,7 +296,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         const Real tube_length = norm2(tdx, tdy);
         if (ph == 2 && ph > pp_eff + 1) rew -= goal * Real(3);  // july:1149
         const Real ex = s.x - wf[GMPE_WF_ENT_X], ey = s.y - wf[GMPE_WF_ENT_Y];
-        const Real proj = ex * (tdx / tube_length) + ey * (tdy / tube_length);
+        const Real proj = ex * div_(tdx, tube_length) + ey * div_(tdy, tube_length);
         const Real edist = norm2(ex - proj * tdx, ey - proj * tdy);  // un-normalised direction, july:1154
         if (ph == pp_eff + 1 && pr == ph - 1) {                      // july:1156-1160
           if (ph == 1 && Real(0) <= proj && proj < Real(0.1) * tube_length && edist < Real(0.2) * tube_length) rew += goal * Real(3);
@@ -440,7 +440,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
 #pragma unroll
         for (int k = 0; k < N; ++k)
           if (k == i) { s = pl.s[k]; lmi = pl.lm[k]; }
-        aux.y = c.max_speed > 0 ? norm2(s.x - lmi.x, s.y - lmi.y) / Real(c.max_speed) : Real(INFINITY);  // min_time july:941-951
+        aux.y = c.max_speed > 0 ? div_(norm2(s.x - lmi.x, s.y - lmi.y), Real(c.max_speed)) : Real(INFINITY);  // min_time july:941-951
       }
       // persist the world-level arrays
       if (i == 0) {

@@ -61,10 +61,18 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, int64_t world, u
 
 // ---- scalar math --------------------------------------------------------------------
 __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
-// sqrtf / the fp32 quotient branch to a ~35-instruction slow path when an operand is zero or
-// denormal (FCHK); zeros are common here (coincident landmarks, agents at rest, counters
-// that have not moved), so they are answered up front.  Results are unchanged.
-__device__ __forceinline__ float sqrt_(float x) { return x == 0.0f ? x : sqrtf(x); }
+// fp32 production arithmetic.  IEEE sqrtf and the IEEE fp32 quotient cost 10-12 instructions
+// each plus a ~35-instruction out-of-line slow path that is taken whenever an operand is
+// zero or denormal (coincident landmarks, agents at rest, counters that have not moved) --
+// on this path they were a quarter of all issued instructions (profiles/r1g_*).  The fp32
+// instantiation therefore uses the SFU forms (sqrt.approx, div.approx: <= 2 ulp), which is
+// three orders of magnitude inside the 1e-5 relative tolerance the path is specified to
+// (BASELINE.json north_star); the fp64 strict-parity instantiation stays IEEE throughout.
+__device__ __forceinline__ float sqrt_(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
 __device__ __forceinline__ double abs_(double x) { return fabs(x); }
@@ -79,8 +87,10 @@ __device__ __forceinline__ double log1p_(double x) { return log1p(x); }
 __device__ __forceinline__ bool isnan_(float x) { return isnan(x); }
 __device__ __forceinline__ bool isnan_(double x) { return isnan(x); }
 
-// a / b for finite b > 0 (see sqrt_)
-__device__ __forceinline__ float qdiv(float a, float b) { return a == 0.0f ? a : a / b; }
+// quotient (see sqrt_)
+__device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double div_(double a, double b) { return a / b; }
+__device__ __forceinline__ float qdiv(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double qdiv(double a, double b) { return a / b; }
 
 // np.linalg.norm of a 2-vector; one definition for every distance so that adjacency,
@@ -91,11 +101,10 @@ __device__ __forceinline__ Real norm2(Real x, Real y) { return sqrt_(x * x + y *
 template <typename Real>
 __device__ __forceinline__ Real clip(Real v, Real lo, Real hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// np.logaddexp(0, x)
-template <typename Real>
-__device__ __forceinline__ Real softplus(Real x) {
-  return x > Real(0) ? x + log1p_(exp_(-x)) : log1p_(exp_(x));
-}
+// np.logaddexp(0, x) = max(x, 0) + log1p(exp(-|x|)); fp32: SFU exp / log, absolute error
+// <= 1e-7 (the contact force it scales is O(1))
+__device__ __forceinline__ double softplus(double x) { return x > 0.0 ? x + log1p(exp(-x)) : log1p(exp(x)); }
+__device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.0f) + __logf(1.0f + __expf(-fabsf(x))); }
 
 // the reference casts positions to float32 before projecting on the tube frame (july:624)
 __device__ __forceinline__ float trunc32(float x) { return x; }

@@ -356,9 +356,9 @@ gmpe_step_small_kernel(const __grid_constant__ KParams p) {
 #pragma unroll
           for (int k = a + 1; k < N; ++k) {
             const Real dx = s[a].x - s[k].x, dy = s[a].y - s[k].y, dist = norm2(dx, dy);
-            pen[a][k] = softplus(-(dist - dmin) / km) * km;
-            tx[a][k] = cf * dx / dist;
-            ty[a][k] = cf * dy / dist;
+            pen[a][k] = softplus(div_(-(dist - dmin), km)) * km;
+            tx[a][k] = div_(cf * dx, dist);
+            ty[a][k] = div_(cf * dy, dist);
           }
         Real fx[N], fy[N];
 #pragma unroll
@@ -380,7 +380,7 @@ gmpe_step_small_kernel(const __grid_constant__ KParams p) {
             s[i].w = s[i].w * Real(1 - c.damping) + fy[i] * dt;
             if (c.max_speed > 0) {
               const Real speed = sqrt_(s[i].z * s[i].z + s[i].w * s[i].w);
-              if (speed > Real(c.max_speed)) { s[i].z = s[i].z / speed * Real(c.max_speed); s[i].w = s[i].w / speed * Real(c.max_speed); }
+              if (speed > Real(c.max_speed)) { s[i].z = div_(s[i].z, speed) * Real(c.max_speed); s[i].w = div_(s[i].w, speed) * Real(c.max_speed); }
             }
             s[i].x += s[i].z * dt; s[i].y += s[i].w * dt;
             aux[i].x += norm2(s[i].z * dt, s[i].w * dt);
@@ -402,7 +402,7 @@ gmpe_step_small_kernel(const __grid_constant__ KParams p) {
       else {
         vpre[i] = RT<Real>::mk2(s[i].z, s[i].w);
         const Real sp = norm2(s[i].z, s[i].w);  // DoubleIntegratorXYState.theta = arctan2(vy, vx), core.py:188-189
-        if (sp > Real(0)) { hx[i] = s[i].z / sp; hy[i] = s[i].w / sp; }
+        if (sp > Real(0)) { hx[i] = div_(s[i].z, sp); hy[i] = div_(s[i].w, sp); }
       }
       vpost[i] = vpre[i];
     }
@@ -477,7 +477,7 @@ gmpe_step_small_kernel(const __grid_constant__ KParams p) {
           const Real tube_length = norm2(tdx, tdy);
           if (ph == 2 && ph > pp_eff + 1) r -= goal * Real(3);  // july:1149
           const Real ex = px - wf[GMPE_WF_ENT_X], ey = py - wf[GMPE_WF_ENT_Y];
-          const Real proj = ex * (tdx / tube_length) + ey * (tdy / tube_length);
+          const Real proj = ex * div_(tdx, tube_length) + ey * div_(tdy, tube_length);
           const Real edist = norm2(ex - proj * tdx, ey - proj * tdy);  // un-normalised direction, july:1154
           if (ph == pp_eff + 1 && prc == ph - 1) {                     // july:1156-1160
             if (ph == 1 && Real(0) <= proj && proj < Real(0.1) * tube_length && edist < Real(0.2) * tube_length) r += goal * Real(3);
@@ -657,7 +657,7 @@ gmpe_step_small_kernel(const __grid_constant__ KParams p) {
         for (int i = 0; i < N; ++i) { s[i] = pl.s[i]; lm[i] = pl.lm[i]; }
 #pragma unroll
         for (int i = 0; i < N; ++i)  // min_time july:941-951
-          aux[i].y = c.max_speed > 0 ? norm2(s[i].x - lm[i].x, s[i].y - lm[i].y) / Real(c.max_speed) : Real(INFINITY);
+          aux[i].y = c.max_speed > 0 ? div_(norm2(s[i].x - lm[i].x, s[i].y - lm[i].y), Real(c.max_speed)) : Real(INFINITY);
       }
       // persist the world-level arrays
       Real* gw_ = g_wf + (size_t)b * GMPE_WORLD_F;

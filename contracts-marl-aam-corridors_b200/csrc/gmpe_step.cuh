@@ -249,7 +249,7 @@ __device__ __forceinline__ int tube_phase(const Real* wf, Real px, Real py, int&
   bool in_tube = (-eps <= s) && (s <= L + eps) && lat;
   Real tdx = wf[GMPE_WF_EXIT_X] - wf[GMPE_WF_ENT_X], tdy = wf[GMPE_WF_EXIT_Y] - wf[GMPE_WF_ENT_Y];
   Real tn = norm2(tdx, tdy);
-  tdx /= tn; tdy /= tn;
+  tdx = div_(tdx, tn); tdy = div_(tdy, tn);
   bool passed = ((px - wf[GMPE_WF_EXIT_X]) * tdx + (py - wf[GMPE_WF_EXIT_Y]) * tdy) > Real(0);
   Real gf = Real(0.08) * L, gb = Real(0.02) * L;
   bool gate = (-gb - eps <= s) && (s <= gf + eps) && lat;
@@ -302,8 +302,8 @@ __device__ __forceinline__ void wall_force(const GmpeConfig& c, const Real* w, R
   bool classic = (c.flags & GMPE_FLAG_CLASSIC_CONTACT) != 0;
   Real k = Real(classic ? c.contact_margin : c.wall_contact_margin);
   Real cf = Real(classic ? c.contact_force : c.wall_contact_force);
-  Real pen = softplus(-(dist - dist_min) / k) * k;
-  Real fm = cf * delta / dist * pen;
+  Real pen = softplus(div_(-(dist - dist_min), k)) * k;
+  Real fm = div_(cf * delta, dist) * pen;
   Real fperp = ct * fm, fpar = st * abs_(fm);
   if (horiz) { fx += fpar; fy += fperp; } else { fx += fperp; fy += fpar; }
 }
@@ -535,9 +535,9 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
             Real dx = s.x - q.x, dy = s.y - q.y, dist = norm2(dx, dy);
             Real size_k = k >= N + L + O ? Real(c.wall_width) : Real(c.entity_size);
             Real dmin = classic ? Real(c.entity_size) + size_k : Real(c.separation_dist);
-            Real pen = softplus(-(dist - dmin) / km) * km;
-            fx = cf * dx / dist * pen + fx;
-            fy = cf * dy / dist * pen + fy;
+            Real pen = softplus(div_(-(dist - dmin), km)) * km;
+            fx = div_(cf * dx, dist) * pen + fx;
+            fy = div_(cf * dy, dist) * pen + fy;
           }
           for (int q = 0; q < W; ++q) wall_force<Real>(c, wl_w + q * GMPE_WALL_F, s.x, s.y, fx, fy);
           if (classic || !st_pre) {  // integrate_state core.py:827-845; done agents freeze
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
             s.w = s.w * Real(1 - c.damping) + fy * dt;
             if (c.max_speed > 0) {
               Real speed = sqrt_(s.z * s.z + s.w * s.w);
-              if (speed > Real(c.max_speed)) { s.z = s.z / speed * Real(c.max_speed); s.w = s.w / speed * Real(c.max_speed); }
+              if (speed > Real(c.max_speed)) { s.z = div_(s.z, speed) * Real(c.max_speed); s.w = div_(s.w, speed) * Real(c.max_speed); }
             }
             s.x += s.z * dt; s.y += s.w * dt;
             aux.x += norm2(s.z * dt, s.w * dt);
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
         else {
           vpre = RT<Real>::mk2(s.z, s.w);
           Real sp = norm2(s.z, s.w);  // DoubleIntegratorXYState.theta = arctan2(vy, vx), core.py:188-189
-          if (sp > Real(0)) { hx = s.z / sp; hy = s.w / sp; }
+          if (sp > Real(0)) { hx = div_(s.z, sp); hy = div_(s.w, sp); }
         }
         pos_w[i] = RT<Real>::mk2(s.x, s.y);
         sm.velpre[tid] = vpre;
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
         Real tube_length = norm2(tdx, tdy);
         if (ph == 2 && ph > pp_eff + 1) rew -= goal * Real(3);  // july:1149
         Real ex = s.x - wfw[GMPE_WF_ENT_X], ey = s.y - wfw[GMPE_WF_ENT_Y];
-        Real proj = ex * (tdx / tube_length) + ey * (tdy / tube_length);
+        Real proj = ex * div_(tdx, tube_length) + ey * div_(tdy, tube_length);
         Real edist = norm2(ex - proj * tdx, ey - proj * tdy);  // un-normalised direction, july:1154
         if (ph == pp_eff + 1 && phase_reached == ph - 1) {     // july:1156-1160
           if (ph == 1 && Real(0) <= proj && proj < Real(0.1) * tube_length && edist < Real(0.2) * tube_length) rew += goal * Real(3);
@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
       } else {
         s = sm.nst[tid];
         V2 g = pos_w[N + i];
-        aux.y = c.max_speed > 0 ? norm2(s.x - g.x, s.y - g.y) / Real(c.max_speed) : Real(INFINITY);  // min_time july:941-951
+        aux.y = c.max_speed > 0 ? div_(norm2(s.x - g.x, s.y - g.y), Real(c.max_speed)) : Real(INFINITY);  // min_time july:941-951
       }
       aux.x = Real(0);
       st_post = 0; phase_reached = 0; goal_reached = 0;
