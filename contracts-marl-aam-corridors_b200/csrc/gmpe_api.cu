@@ -25,6 +25,7 @@ struct gmpe_ctx {
   int stage_graph;
   int small;  // KERNEL_TILE (gmpe_step.cuh) / KERNEL_WORLD (gmpe_small.cuh) / KERNEL_COOP (gmpe_coop.cuh)
   const void* fn;
+  void* act_tab;  // device copy of the _set_action table (Real [32][2]); the only memory the library owns
   int64_t launches;
   std::string err;
 };
@@ -159,6 +160,7 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
   h->cfg = *cfg;
   h->device = device;
   h->launches = 0;
+  h->act_tab = nullptr;
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(device);
@@ -224,9 +226,44 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
     return fail(nullptr, GMPE_E_CUDA, m);
   }
   if (per_sm < 1) per_sm = 1;
+  {  // _set_action (environment.py:336-475) evaluated once per action index
+    double td[64];
+    float tf[64];
+    for (int a = 0; a < 32; ++a) {
+      double u0 = 0.0, u1 = 0.0;
+      if (a < cfg->total_actions) decode_action<double>(h->cfg, a, u0, u1);
+      td[2 * a] = u0; td[2 * a + 1] = u1;
+      float f0 = 0.f, f1 = 0.f;
+      if (a < cfg->total_actions) decode_action<float>(h->cfg, a, f0, f1);
+      tf[2 * a] = f0; tf[2 * a + 1] = f1;
+    }
+    const size_t nbytes = f64 ? sizeof(td) : sizeof(tf);
+    e = cudaMalloc(&h->act_tab, nbytes);
+    if (e == cudaSuccess) e = cudaMemcpy(h->act_tab, f64 ? (const void*)td : (const void*)tf, nbytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      std::string m = std::string("gmpe_create: ") + cudaGetErrorString(e);
+      if (h->act_tab) cudaFree(h->act_tab);
+      delete h;
+      cudaSetDevice(prev);
+      return fail(nullptr, GMPE_E_CUDA, m);
+    }
+  }
   // persistent grid: one wave of resident CTAs, tiles strided over it (148 SMs on B200)
   int64_t g = (int64_t)h->sm_count * per_sm;
-  h->grid = (int)(units < g ? units : g);
+  // tile / thread-per-world kernels: persistent grid, one wave of resident CTAs strided over the
+  // batch; lane-per-agent kernel: one warp per group of worlds, balanced by the block scheduler
+  // Persistent grid: at most one wave of resident CTAs, units strided over it.  When the batch
+  // needs r > 1 rounds the grid is shrunk to ceil(units / r) CTAs so that every CTA runs exactly
+  // r rounds (a last round that only a few CTAs take part in leaves the SMs idle).
+  bool persistent = true;
+  if (const char* t = getenv("GMPE_PERSISTENT")) persistent = atoi(t) != 0;  // tuning knob (tools/ab.py)
+  if (units <= g || !persistent) {
+    h->grid = units;
+  } else {
+    const int64_t rounds = (units + g - 1) / g;
+    h->grid = (int)((units + rounds - 1) / rounds);
+    if (const char* t = getenv("GMPE_BALANCED")) if (!atoi(t)) h->grid = (int)g;
+  }
   cudaSetDevice(prev);
   *out = h;
   return GMPE_OK;
@@ -234,6 +271,13 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
 
 int gmpe_destroy(gmpe_handle h) {
   if (!h) return GMPE_E_NULL;
+  if (h->act_tab) {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(h->device);
+    cudaFree(h->act_tab);
+    cudaSetDevice(prev);
+  }
   delete h;
   return GMPE_OK;
 }
@@ -278,6 +322,10 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   p.F = c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
   p.dN = FastDiv::make(N); p.dE = FastDiv::make(p.E); p.dL = FastDiv::make(L); p.dO = FastDiv::make(O);
   p.dW = FastDiv::make(W); p.dF = FastDiv::make(p.F); p.d16 = FastDiv::make(16);
+#ifdef GMPE_EXPERIMENTS
+  if (const char* t = getenv("GMPE_XMODE")) p.xmode = atoi(t);
+#endif
+  p.act_tab = h->act_tab;
   p.dE2 = FastDiv::make(p.E * 2); p.dNE2 = FastDiv::make(N * p.E * 2); p.dEE = FastDiv::make(p.E * p.E);
   int prev = 0;
   cudaGetDevice(&prev);

@@ -34,6 +34,11 @@ namespace gmpe {
 #ifndef GMPE_COOP_MINBLOCKS_F64
 #define GMPE_COOP_MINBLOCKS_F64 2
 #endif
+// 1: adjacency rows (and even-width obs rows) leave the lane directly as 64/128-bit stores;
+// 0: staged in the slab and streamed out as contiguous 128-bit stores
+#ifndef GMPE_COOP_DIRECT_SMALL_ROWS
+#define GMPE_COOP_DIRECT_SMALL_ROWS 0
+#endif
 
 template <typename Real, int SCEN, int N>
 struct CoopTraits {
@@ -91,24 +96,17 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
   constexpr int E = T::E, EE = T::EE, CAP = T::CAP, F = T::F, WPW = T::WPW, AL = T::AL;
   constexpr bool july = SCEN == GMPE_SCEN_JULY_TUBE;
   extern __shared__ __align__(32) unsigned char smem_raw[];
-  __shared__ Real acttab[2 * 32];
-
   const GmpeConfig& c = p.c;
   const int B = c.num_worlds;
   const bool heading = c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR;
   const bool do_info = (c.flags & GMPE_FLAG_INFO) != 0;
+#ifdef GMPE_EXPERIMENTS
+  const bool step_mode = p.mode == MODE_STEP && p.xmode != 1;
+#else
   const bool step_mode = p.mode == MODE_STEP;
+#endif
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* slab = smem_raw + (size_t)warp * T::SLAB_BYTES;
-
-  // _set_action table (environment.py:336-475): identical arithmetic to decode_action
-  if (threadIdx.x < 32) {
-    Real u0 = Real(0), u1 = Real(0);
-    if ((int)threadIdx.x < c.total_actions) decode_action<Real>(c, threadIdx.x, u0, u1);
-    acttab[2 * threadIdx.x] = u0;
-    acttab[2 * threadIdx.x + 1] = u1;
-  }
-  __syncthreads();
 
   Real* g_as = (Real*)p.st.agent_state;
   Real* g_aux = (Real*)p.st.agent_aux;
@@ -180,7 +178,9 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     if (step_mode) {
       // ---------------- stage 2 + stage 1: action decode and physics --------------------
       const int a = p.act[ga];
-      const Real u0 = acttab[2 * (a & 31)], u1 = acttab[2 * (a & 31) + 1];
+      // _set_action (environment.py:336-475): table evaluated on the host, 256 bytes, L1-resident
+      const V2 u = ((const V2*)p.act_tab)[a & 31];
+      const Real u0 = u.x, u1 = u.y;
       if (c.physics == GMPE_PHYS_FORCE) {
         // classic step order (onpolicy/envs/mpe/core.py:183-202) with the force functions of
         // multiagent/core.py:766-984, accumulated over the other agents in entity order
@@ -417,6 +417,9 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       const bool m = p.env_mask ? (p.env_mask[b] != 0) : true;
       rs = valid && m;
       wr = rs;
+#ifdef GMPE_EXPERIMENTS
+      if (p.xmode == 1) rs = false;
+#endif
     }
 
     // ---------------- reset (auto-reset of finished worlds, or MODE_RESET) -------------------
@@ -482,6 +485,10 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         dal[k] = norm2(s.x - LX[k], s.y - LY[k]);
       }
     }
+#ifdef GMPE_EXPERIMENTS
+    if (p.xmode == 1) wr = valid;
+    if (p.xmode == 2) wr = false;
+#endif
     const uint32_t lane_wr = __ballot_sync(0xffffffffu, wr);
     if (lane_wr == 0) continue;
     // world-level write mask (bit w = world w of this warp) and "every world of the warp"
@@ -521,13 +528,17 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       }
     }
 
-    // ---------------- emission: obs rows + adjacency (staged, round A) -------------------------
+    // ---------------- emission: obs rows + adjacency ------------------------------------------
     Real* g_obs = p.out.obs ? (Real*)p.out.obs + (size_t)wbase * N * F : nullptr;
+    // obs rows whose byte length is a multiple of 8 (navigation: 6 Reals) leave the lane as
+    // 64/128-bit stores; the 19-wide july rows are staged and streamed out as one span
+    constexpr bool obs_direct = GMPE_COOP_DIRECT_SMALL_ROWS && (F % 2) == 0;
+    constexpr bool adj_direct = GMPE_COOP_DIRECT_SMALL_ROWS != 0;
     Real* g_adj = p.out.adj ? (Real*)p.out.adj + (size_t)wbase * EE : nullptr;
     unsigned char* obs_region = slab;
     unsigned char* adj_region = slab + T::OBS_BYTES;
-    Real* obs_s = reinterpret_cast<Real*>(obs_region + (reinterpret_cast<size_t>(g_obs) & 15)) + lane * F;
     Real* adj_s = reinterpret_cast<Real*>(adj_region + (reinterpret_cast<size_t>(g_adj) & 15)) + wl * EE;
+    Real* obs_s = reinterpret_cast<Real*>(obs_region + (reinterpret_cast<size_t>(g_obs) & 15)) + lane * F;
     // rows i and N + i of the masked distance matrix (july:1625-1648): done agents and the
     // landmark a done agent reached (goal_tracker[l] == l) are disconnected
     Real row_a[E], row_l[E];
@@ -563,17 +574,32 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         o[15] = wf[GMPE_WF_EXIT_X] - s.x; o[16] = wf[GMPE_WF_EXIT_Y] - s.y;
         o[17] = wf[GMPE_WF_WIDTH];
         o[18] = Real(ph_obs);
+      } else if (obs_direct) {
+        if (wr && g_obs) {
+          V2* o = reinterpret_cast<V2*>((Real*)p.out.obs + ga * F);
+          o[0] = vpre; o[1] = RT<Real>::mk2(s.x, s.y); o[2] = RT<Real>::mk2(lmi.x - s.x, lmi.y - s.y);
+        }
       } else {
         Real* o = obs_s;
         o[0] = vpre.x; o[1] = vpre.y; o[2] = s.x; o[3] = s.y; o[4] = lmi.x - s.x; o[5] = lmi.y - s.y;
       }
+      if (!adj_direct) {
 #pragma unroll
-      for (int q = 0; q < E; ++q) { adj_s[i * E + q] = row_a[q]; adj_s[(N + i) * E + q] = row_l[q]; }
+        for (int q = 0; q < E; ++q) { adj_s[i * E + q] = row_a[q]; adj_s[(N + i) * E + q] = row_l[q]; }
+      }
     }
-    __syncwarp();
-    if (g_obs) copy_span<Real, N * F>(g_obs, obs_region, nwv * N * F, all_worlds, wmask, lane);
-    if (g_adj) copy_span<Real, EE>(g_adj, adj_region, nwv * EE, all_worlds, wmask, lane);
-    __syncwarp();
+    if (adj_direct && wr && p.out.adj) {  // two rows of E Reals each, 8/16-byte aligned (E is even)
+      V2* ra = reinterpret_cast<V2*>((Real*)p.out.adj + (size_t)b * EE + (size_t)i * E);
+      V2* rl = reinterpret_cast<V2*>((Real*)p.out.adj + (size_t)b * EE + (size_t)(N + i) * E);
+#pragma unroll
+      for (int q = 0; q < N; ++q) { ra[q] = RT<Real>::mk2(row_a[2 * q], row_a[2 * q + 1]); rl[q] = RT<Real>::mk2(row_l[2 * q], row_l[2 * q + 1]); }
+    }
+    if (!obs_direct || !adj_direct) {
+      __syncwarp();
+      if (!obs_direct && g_obs) copy_span<Real, N * F>(g_obs, obs_region, nwv * N * F, all_worlds, wmask, lane);
+      if (!adj_direct && g_adj) copy_span<Real, EE>(g_adj, adj_region, nwv * EE, all_worlds, wmask, lane);
+      __syncwarp();
+    }
 
     // ---------------- emission: edge lists (staged, round B, once per list) ---------------------
     // update_graph (july:1651-1670): (d <= max_edge_dist) & (d > 0), row-major COO;
@@ -591,9 +617,6 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       unsigned char* ea_region = slab + T::EIDX_BYTES;
       int32_t* ei_w = reinterpret_cast<int32_t*>(ei_region + (reinterpret_cast<size_t>(g_ei) & 15));
       Real* ea_w = reinterpret_cast<Real*>(ea_region + (reinterpret_cast<size_t>(g_ea) & 15));
-      // -1 / 0 padding of the fixed-capacity buffers
-      for (int q = lane; q < WPW * 2 * CAP; q += 32) ei_w[q] = -1;
-      for (int q = lane; q < WPW * CAP; q += 32) ea_w[q] = Real(0);
       uint32_t on_a = 0, on_l = 0;
 #pragma unroll
       for (int q = 0; q < E; ++q) {
@@ -612,7 +635,12 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         off_l += cak;  // landmark rows follow all agent rows
         n_edges += cak + clk;
       }
-      __syncwarp();
+      // -1 / 0 padding of the fixed-capacity buffers, unless every list of the warp is full
+      if (!__all_sync(0xffffffffu, n_edges == CAP)) {
+        for (int q = lane; q < WPW * 2 * CAP; q += 32) ei_w[q] = -1;
+        for (int q = lane; q < WPW * CAP; q += 32) ea_w[q] = Real(0);
+        __syncwarp();
+      }
       if (lane_used) {
         int32_t* ei = ei_w + wl * 2 * CAP;
         Real* ea = ea_w + wl * CAP;

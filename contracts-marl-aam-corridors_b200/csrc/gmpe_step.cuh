@@ -43,6 +43,8 @@ struct KParams {
   int E, F;       // entities per world, obs width
   int stage_graph; // small worlds: adjacency / edges staged in shared memory (see Smem)
   FastDiv dN, dE, dL, dO, dW, dF, d16, dE2, dNE2, dEE;
+  int xmode;       // GMPE_EXPERIMENTS builds only (tools/ab.py): 1 = skip physics/reward, 2 = skip emission
+  const void* act_tab;  // Real [32][2]: _set_action table (decode_action evaluated on the host), device memory owned by the handle
 };
 
 // ---- shared memory carve-up --------------------------------------------------------
@@ -165,7 +167,7 @@ __device__ __forceinline__ void copy_out(T* __restrict__ dst, const T* __restric
 
 // MultiAgentBaseEnv._set_action (environment.py:336-475), index form of the one-hot
 template <typename Real>
-__device__ __forceinline__ void decode_action(const GmpeConfig& c, int a, Real& u0, Real& u1) {
+__host__ __device__ __forceinline__ void decode_action(const GmpeConfig& c, int a, Real& u0, Real& u1) {
   double x = 0.0, y = 0.0;
   if (c.dynamics == GMPE_DYN_DOUBLE_INTEGRATOR) {
     if (c.total_actions == 9) {  // environment.py:382-392
