@@ -303,6 +303,10 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   if (mode == MODE_STEP && (!act || !out->reward || !out->done)) return fail(h, GMPE_E_NULL, "gmpe_step needs action_idx, out.reward and out.done");
   if ((c.flags & GMPE_FLAG_ENV_EDGES) && out->edge_index && (!out->edge_attr || !out->num_edges)) return fail(h, GMPE_E_NULL, "edge_attr / num_edges missing");
   if ((c.flags & GMPE_FLAG_GNN_EDGES) && out->gnn_edge_index && (!out->gnn_edge_attr || !out->gnn_num_edges)) return fail(h, GMPE_E_NULL, "gnn_edge_attr / gnn_num_edges missing");
+  // feature rows leave the SM as 256-bit stores (store_row8): torch / cudaMalloc buffers are
+  // 256-byte aligned, an arbitrary caller pointer must at least be 32-byte aligned
+  if ((reinterpret_cast<size_t>(out->node_obs) & 31) || (reinterpret_cast<size_t>(out->info) & 31))
+    return fail(h, GMPE_E_INVALID, "out.node_obs and out.info must be 32-byte aligned");
   KParams p;
   memset(&p, 0, sizeof(p));
   p.c = c;

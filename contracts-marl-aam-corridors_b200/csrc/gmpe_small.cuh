@@ -125,19 +125,6 @@ __device__ __forceinline__ void copy_flat(T* __restrict__ g, const T* __restrict
   }
 }
 
-// One feature row of 8 Reals with 256-bit stores (sm_100: STG.E.ENL2.256): a lane writes
-// whole 32-byte sectors, so per-world rows need no staging to reach the memory system as
-// full-sector writes.  p must be 32-byte aligned.
-__device__ __forceinline__ void store_row8(float* p, const float (&f)[8]) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]),
-               "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])
-               : "memory");
-}
-__device__ __forceinline__ void store_row8(double* p, const double (&f)[8]) {
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(f[0]), "d"(f[1]), "d"(f[2]), "d"(f[3]) : "memory");
-  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + 4), "d"(f[4]), "d"(f[5]), "d"(f[6]), "d"(f[7]) : "memory");
-}
-
 // ---- placement of one world in registers ---------------------------------------------
 // random_scenario + setup_tube_params (july:440-613), set_landmarks_in_point
 // (utils.py:165-193); navigation placement is defined-by-build.  Draw order and

@@ -77,6 +77,9 @@ struct Smem {
   Real* eattr;                     // [WPB*cap]
   int32_t* gidx;                   // [WPB*2*cap]
   Real* gattr;                     // [WPB*cap]
+  // -- large worlds: per-row edge counts -> exclusive row offsets (row-wise phase B)
+  int32_t* rowoff_env;             // [WPB*E]
+  int32_t* rowoff_gnn;             // [WPB*E]
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -100,6 +103,8 @@ __host__ __device__ inline size_t smem_layout(int wpb, int N, int E, int W, int 
   size_t o_mask = take(wpb * E, 16);
   size_t o_wreset = take(wpb, 16);
   size_t o_wwrite = take(wpb, 16);
+  size_t o_ro_env = take(4 * wpb * E, 16);
+  size_t o_ro_gnn = take(4 * wpb * E, 16);
   o = align_up(o, 32);
   const size_t scratch0 = o;
   size_t o_nst = take(4 * R * wpb * N, 32);
@@ -135,6 +140,8 @@ __host__ __device__ inline size_t smem_layout(int wpb, int N, int E, int W, int 
     s->mask = base + o_mask;
     s->wreset = base + o_wreset;
     s->wwrite = base + o_wwrite;
+    s->rowoff_env = (int32_t*)(base + o_ro_env);
+    s->rowoff_gnn = (int32_t*)(base + o_ro_gnn);
     s->nst = (typename RT<Real>::V4*)(base + o_nst);
     s->obs = (Real*)(base + o_obs);
     s->rew = (Real*)(base + o_rew);
@@ -871,33 +878,62 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
         }
       }
     }
-    // node_obs: [lw][j][k][8] as two 4-vectors per (ego j, entity k)  (july:1694-1771)
-    if (p.out.node_obs) {
+    // node_obs [lw][j][k][8]  (_get_entity_feat_relative, july:1694-1771)
+    // Row-wise generation for large worlds (E >= 64): a warp owns one matrix row and its lanes
+    // walk the entities, so the inner loops carry no index arithmetic.  (Measured on B200:
+    // 951 -> 746 us at E = 128; for E = 44 sub-warp row groups of 16 lanes were slower than
+    // the element-parallel form below, 461 vs 382 us, so smaller worlds keep that.)
+    const bool rowwise = !p.stage_graph && E >= 64;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    constexpr int LPR = 32, rpw = 1;
+    const int sub = 0, sl = lane;
+    if (p.out.node_obs && rowwise) {
+      // consecutive lanes write consecutive 32-byte feature rows with one 256-bit store each
       Real* g_node = (Real*)p.out.node_obs + (size_t)w0 * N * E * 8;
-      const int total = nw * N * E * 2;
+      for (int row = warp * rpw + sub; row < nw * N; row += nwarps * rpw) {
+        uint32_t w, j;
+        p.dN.divmod(row, w, j);
+        if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
+        const V2* pw = sm.pos + w * E;
+        const V2 pe = pw[j], ve = sm.velpost[w * N + j];
+        Real* grow = g_node + (size_t)row * E * 8;
+        for (int k = sl; k < E; k += LPR) {
+          const V2 pk = pw[k];
+          const Real rx = pk.x - pe.x, ry = pk.y - pe.y;
+          if (k < N) {
+            const V2 vk = (k <= (int)j ? sm.velpost : sm.velpre)[w * N + k];
+            const V2 gk = pw[N + k];  // landmark_poses[entity.id] (july:1740)
+            const Real f[8] = {vk.x - ve.x, vk.y - ve.y, rx, ry, gk.x - pe.x, gk.y - pe.y, Real(0), Real(0)};
+            store_row8(grow + (size_t)k * 8, f);
+          } else {
+            const Real ty = k < N + L ? Real(1) : (k < N + L + O ? Real(2) : Real(3));
+            const Real f[8] = {Real(0) - ve.x, Real(0) - ve.y, rx, ry, rx, ry, Real(1), ty};
+            store_row8(grow + (size_t)k * 8, f);
+          }
+        }
+      }
+    } else if (p.out.node_obs) {
+      // smaller worlds: element-parallel over (world, ego j, entity k), one 256-bit store each
+      Real* g_node = (Real*)p.out.node_obs + (size_t)w0 * N * E * 8;
+      const int total = nw * N * E;
       for (int q = tid; q < total; q += nthr) {
-        uint32_t half = q & 1, t = q >> 1, k, t2, j, w;
-        p.dE.divmod(t, t2, k);
+        uint32_t k, t2, j, w;
+        p.dE.divmod(q, t2, k);
         p.dN.divmod(t2, w, j);
         if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
         const V2* pw = sm.pos + w * E;
-        V2 pe = pw[j], pk = pw[k];
-        V4 v;
-        if (half == 0) {
-          V2 ve = sm.velpost[w * N + j];
-          V2 vk = RT<Real>::mk2(0, 0);
-          if (k < (uint32_t)N) vk = (k <= j ? sm.velpost : sm.velpre)[w * N + k];
-          v = RT<Real>::mk4(vk.x - ve.x, vk.y - ve.y, pk.x - pe.x, pk.y - pe.y);
+        const V2 pe = pw[j], pk = pw[k], ve = sm.velpost[w * N + j];
+        const Real rx = pk.x - pe.x, ry = pk.y - pe.y;
+        if (k < (uint32_t)N) {
+          const V2 vk = (k <= j ? sm.velpost : sm.velpre)[w * N + k];
+          const V2 gk = pw[N + k];  // landmark_poses[entity.id] (july:1740)
+          const Real f[8] = {vk.x - ve.x, vk.y - ve.y, rx, ry, gk.x - pe.x, gk.y - pe.y, Real(0), Real(0)};
+          store_row8(g_node + (size_t)q * 8, f);
         } else {
-          if (k < (uint32_t)N) {
-            V2 gk = pw[N + k];  // landmark_poses[entity.id] (july:1740)
-            v = RT<Real>::mk4(gk.x - pe.x, gk.y - pe.y, Real(0), Real(0));
-          } else {
-            Real ty = k < (uint32_t)(N + L) ? Real(1) : (k < (uint32_t)(N + L + O) ? Real(2) : Real(3));
-            v = RT<Real>::mk4(pk.x - pe.x, pk.y - pe.y, Real(1), ty);
-          }
+          const Real ty = k < (uint32_t)(N + L) ? Real(1) : (k < (uint32_t)(N + L + O) ? Real(2) : Real(3));
+          const Real f[8] = {Real(0) - ve.x, Real(0) - ve.y, rx, ry, rx, ry, Real(1), ty};
+          store_row8(g_node + (size_t)q * 8, f);
         }
-        ((V4*)g_node)[q] = v;
       }
     }
     __syncthreads();  // mask ready; phase-A scratch (obs staging, counters) is dead from here on
@@ -960,8 +996,8 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
         copy_out<int32_t>(p.out.gnn_edge_index + (size_t)w0 * 2 * cap, sm.gidx, nw * 2 * cap, tid, nthr);
         copy_out<Real>((Real*)p.out.gnn_edge_attr + (size_t)w0 * cap, sm.gattr, nw * cap, tid, nthr);
       }
-    } else {
-      // ---- large worlds (or reset-only launches): generate in place
+    } else if (!rowwise) {
+      // ---- mid-size worlds (or reset-only launches of small ones): element-parallel, in place
       // adj: masked distance matrix, one copy per world (july:1625-1648)
       if (p.out.adj) {
         Real* g_adj = (Real*)p.out.adj + (size_t)w0 * EE;
@@ -1026,6 +1062,111 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           if (gnn_e) {
             for (int q = n_gnn + lane; q < cap; q += 32) { gi[q] = -1; gi[cap + q] = -1; gea[q] = Real(0); }
             if (lane == 0) p.out.gnn_num_edges[gb] = n_gnn;
+          }
+        }
+      }
+    } else {
+      // ---- large worlds (E >= 64): row-wise.  Pass 1 writes the masked distance row (july:1625-1648,
+      // one copy per world) and counts the row's edges; a shuffle scan turns the
+      // counts into row offsets; pass 2 recomputes the row and stream-compacts it (ballot +
+      // popc within the row's lane group) into the fixed-capacity buffers in row-major order
+      // (update_graph july:1660-1665; process_adj gnn_new.py:339).
+      const unsigned grp_mask = LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u);
+      const unsigned lt_mask = (1u << sl) - 1u;
+      const int nrows = nw * E;
+      for (int row0 = warp * rpw; row0 < nrows; row0 += nwarps * rpw) {
+        const int row = row0 + sub;
+        uint32_t w = 0, r = 0;
+        bool live = row < nrows;
+        if (live) { p.dE.divmod(row, w, r); live = p.mode == MODE_STEP || sm.wwrite[w]; }
+        const V2* pw = sm.pos + w * E;
+        const uint8_t* mk = sm.mask + w * E;
+        const V2 a = pw[r];
+        const bool mr = mk[r] != 0;
+        Real* g_row = (live && p.out.adj) ? (Real*)p.out.adj + ((size_t)(w0 + w) * E + r) * E : nullptr;
+        int n_env = 0, n_gnn = 0;
+        for (int c0 = 0; c0 < E; c0 += LPR) {
+          const int cc = c0 + sl;
+          Real d = Real(0);
+          if (live && cc < E) {
+            const V2 bb = pw[cc];
+            d = ((int)r == cc || mr || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
+            if (g_row) g_row[cc] = d;
+          }
+          if (env_e) n_env += __popc((__ballot_sync(0xffffffffu, d > Real(0) && d <= thr_env) >> (sub * LPR)) & grp_mask);
+          if (gnn_e) { const float df = (float)d; n_gnn += __popc((__ballot_sync(0xffffffffu, df > 0.0f && df < thr_gnn) >> (sub * LPR)) & grp_mask); }
+        }
+        if (live && sl == 0) { sm.rowoff_env[row] = n_env; sm.rowoff_gnn[row] = n_gnn; }
+      }
+      if (env_e || gnn_e) {
+        __syncthreads();
+        for (int w = warp; w < nw; w += nwarps) {  // exclusive scan of the row counts, per world
+          if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
+          int run_env = 0, run_gnn = 0;
+          for (int r0 = 0; r0 < E; r0 += 32) {
+            const int r = r0 + lane;
+            const int ve_ = r < E ? sm.rowoff_env[w * E + r] : 0, vg_ = r < E ? sm.rowoff_gnn[w * E + r] : 0;
+            int ie = ve_, ig = vg_;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int te = __shfl_up_sync(0xffffffffu, ie, o), tg = __shfl_up_sync(0xffffffffu, ig, o);
+              if (lane >= o) { ie += te; ig += tg; }
+            }
+            if (r < E) { sm.rowoff_env[w * E + r] = run_env + ie - ve_; sm.rowoff_gnn[w * E + r] = run_gnn + ig - vg_; }
+            run_env += __shfl_sync(0xffffffffu, ie, 31);
+            run_gnn += __shfl_sync(0xffffffffu, ig, 31);
+          }
+          const size_t gb = (size_t)(w0 + w);
+          // -1 / 0 padding behind the last edge
+          if (env_e) {
+            int32_t* ei = p.out.edge_index + gb * 2 * cap;
+            Real* ea = (Real*)p.out.edge_attr + gb * cap;
+            for (int q = run_env + lane; q < cap; q += 32) { ei[q] = -1; ei[cap + q] = -1; ea[q] = Real(0); }
+            if (lane == 0) p.out.num_edges[gb] = run_env;
+          }
+          if (gnn_e) {
+            int32_t* gi = p.out.gnn_edge_index + gb * 2 * cap;
+            Real* gea = (Real*)p.out.gnn_edge_attr + gb * cap;
+            for (int q = run_gnn + lane; q < cap; q += 32) { gi[q] = -1; gi[cap + q] = -1; gea[q] = Real(0); }
+            if (lane == 0) p.out.gnn_num_edges[gb] = run_gnn;
+          }
+        }
+        __syncthreads();
+        for (int row0 = warp * rpw; row0 < nrows; row0 += nwarps * rpw) {
+          const int row = row0 + sub;
+          uint32_t w = 0, r = 0;
+          bool live = row < nrows;
+          if (live) { p.dE.divmod(row, w, r); live = p.mode == MODE_STEP || sm.wwrite[w]; }
+          const V2* pw = sm.pos + w * E;
+          const uint8_t* mk = sm.mask + w * E;
+          const V2 a = pw[r];
+          const bool mr = mk[r] != 0;
+          const size_t gb = (size_t)(w0 + w);
+          int32_t* ei = env_e ? p.out.edge_index + gb * 2 * cap : nullptr;
+          Real* ea = env_e ? (Real*)p.out.edge_attr + gb * cap : nullptr;
+          int32_t* gi = gnn_e ? p.out.gnn_edge_index + gb * 2 * cap : nullptr;
+          Real* gea = gnn_e ? (Real*)p.out.gnn_edge_attr + gb * cap : nullptr;
+          int b_env = live ? sm.rowoff_env[row] : 0, b_gnn = live ? sm.rowoff_gnn[row] : 0;
+          for (int c0 = 0; c0 < E; c0 += LPR) {
+            const int cc = c0 + sl;
+            Real d = Real(0);
+            if (live && cc < E) {
+              const V2 bb = pw[cc];
+              d = ((int)r == cc || mr || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
+            }
+            if (env_e) {
+              const bool on = d > Real(0) && d <= thr_env;
+              const unsigned m = (__ballot_sync(0xffffffffu, on) >> (sub * LPR)) & grp_mask;
+              if (on) { const int slot = b_env + __popc(m & lt_mask); ei[slot] = (int32_t)r; ei[cap + slot] = cc; ea[slot] = d; }
+              b_env += __popc(m);
+            }
+            if (gnn_e) {
+              const float df = (float)d;
+              const bool on = df > 0.0f && df < thr_gnn;
+              const unsigned m = (__ballot_sync(0xffffffffu, on) >> (sub * LPR)) & grp_mask;
+              if (on) { const int slot = b_gnn + __popc(m & lt_mask); gi[slot] = (int32_t)r; gi[cap + slot] = cc; gea[slot] = Real(df); }
+              b_gnn += __popc(m);
+            }
           }
         }
       }
