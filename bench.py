@@ -136,6 +136,17 @@ def cpu_leg(cfg_args, worlds, steps, warmup, nthreads, max_seconds=25.0):
     return worlds * cfg.num_agents * done / dt, done, dt / done * 1e3
 
 
+def workload_config(opts, wl, args, Bg, world):
+    """The `config` object both arms print (the reference arm runs on this arm's config)."""
+    return {"workload": opts.workload, "scenario": args.scenario_name, "worlds_per_gpu": Bg,
+            "worlds_total": Bg * world, "num_agents": args.num_agents, "num_landmarks": args.num_landmarks,
+            "num_obstacles": args.num_obstacles, "num_walls": args.num_walls,
+            "episode_length": args.episode_length, "actions": "seeded uniform random discrete, resident in HBM",
+            "l2": "flushed before every timed step (256 MiB memset outside the event pair); "
+                  "per-step CUDA events on the launching stream",
+            "outputs": "obs,node_obs,adj,reward,done,info,env edges", "parallelism": f"dp{world} (sharded worlds)"}
+
+
 def run_reference(opts):
     """--impl reference: the reference's own algorithm for this path on the box's host cores.
     The reference is pure Python and cannot travel to the GPU box, so this arm runs the C
@@ -148,12 +159,16 @@ def run_reference(opts):
     cores = os.cpu_count() or 1
     value, done, ms = cpu_leg(wl["args"], worlds, opts.steps, max(opts.warmup, 1), cores, max_seconds=120.0)
     N = wl["args"]["num_agents"]
+    from gmpe_b200 import default_args
+    cfgd = workload_config(opts, wl, default_args(**wl["args"]), worlds, 1)
+    cfgd["actions"] = "seeded uniform random discrete (host)"
+    cfgd["l2"] = "n/a (host cores)"
+    cfgd["parallelism"] = f"{cores} pthreads over worlds"
     line = {
         "impl": "reference", "metric": "agent-steps/sec (env step + graph obs)", "value": value,
         "unit": "agent-steps/s", "n_gpus": opts.gpus, "steps": done, "warmup": opts.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": opts.workload, "worlds": worlds, "num_agents": N,
-                   "scenario": wl["args"]["scenario_name"], "episode_length": wl["args"]["episode_length"]},
+        "config": cfgd,
         "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{done} steps of the full {worlds}-world batch, {cores} pthreads, C port of the "
                                    "reference step (oracle/gmpe_oracle.c)"},
@@ -234,6 +249,7 @@ def run_ours(opts):
 
     # roofline of the dominant (only) kernel of the step
     abytes = eng.algorithmic_bytes_per_env_step() * Bg
+    kernel_name = eng.kernel_name
     peak, peak_src = load_peaks()
     kernel_ms = float(per_step_ms.mean())
     achieved = abytes / (kernel_ms * 1e-3) / 1e9
@@ -244,6 +260,25 @@ def run_ours(opts):
             traffic = json.load(open(tp)).get(opts.workload)
         except Exception:
             traffic = None
+    # context for the fraction: a plain device copy moving the SAME number of bytes (half read,
+    # half written), timed exactly like a step.  MEASURED_PEAKS.json was taken on 1 GiB copies;
+    # a launch of ~100 MB cannot reach that figure (launch ramp + DRAM pipeline fill).
+    half = max(abytes // 2 // 16 * 16, 16)
+    csrc = torch.empty(half, dtype=torch.uint8, device=dev)
+    cdst = torch.empty(half, dtype=torch.uint8, device=dev)
+    cts = []
+    for t in range(13):
+        flush.zero_()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        cdst.copy_(csrc)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        if t >= 3:
+            cts.append(a0.elapsed_time(a1))
+    copy_ms = float(np.median(cts))
+    copy_gbs = 2 * half / (copy_ms * 1e-3) / 1e9
+    del csrc, cdst
 
     # e2e through the reference-facing vec env with host buffers
     eng.close()
@@ -263,7 +298,7 @@ def run_ours(opts):
     sink = 0.0
     for t in range(Ke):
         o = venv.step(onehots[t % 4], 0)
-        sink += float(o[4][0, 0])  # touch the host result
+        sink += float(o[4].reshape(-1)[0])  # touch the host result
     torch.cuda.synchronize()
     e2e_s = gdist.max_over_ranks(time.perf_counter() - t0, dev)
     e2e_value = world * Bg * N * Ke / e2e_s
@@ -284,20 +319,16 @@ def run_ours(opts):
         "metric": "agent-steps/sec (env step + graph obs)", "value": value, "unit": "agent-steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": opts.workload, "scenario": args.scenario_name, "worlds_per_gpu": Bg,
-                   "worlds_total": Bg * world, "num_agents": N, "num_landmarks": args.num_landmarks,
-                   "num_obstacles": args.num_obstacles, "num_walls": args.num_walls,
-                   "episode_length": args.episode_length, "actions": "seeded uniform random discrete, resident in HBM",
-                   "l2": "flushed before every timed step (256 MiB memset outside the event pair); "
-                         "per-step CUDA events on the launching stream",
-                   "outputs": "obs,node_obs,adj,reward,done,info,env edges", "parallelism": f"dp{world} (sharded worlds)"},
+        "config": workload_config(opts, wl, args, Bg, world),
         "env_steps_per_s": value / N,
         "hot_l2": {"ms_per_step": hot_ms, "value": world * Bg * N / (hot_ms * 1e-3),
                    "note": "K steps back to back without the flush (rollout mode)"},
         "wall_s_timed_region": t_wall,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "gmpe_step_kernel<float>",
-                     "algorithmic_bytes_per_launch": abytes, "kernel_ms": kernel_ms},
+                     "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name + "<float>",
+                     "algorithmic_bytes_per_launch": abytes, "kernel_ms": kernel_ms,
+                     "copy_same_bytes": {"ms": copy_ms, "gbs": copy_gbs, "frac_of_it": achieved / copy_gbs,
+                                         "note": "torch copy_ of the same byte count, same flush + event timing"}},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "steps": Ke,

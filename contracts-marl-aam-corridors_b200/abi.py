@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # error codes
 OK, E_INVALID, E_CUDA, E_NULL = 0, -1, -2, -3
@@ -108,6 +108,7 @@ class GmpeStepInject(C.Structure):
 EXPORTED_SYMBOLS = (
     "gmpe_abi_version", "gmpe_create", "gmpe_destroy", "gmpe_last_error", "gmpe_layout",
     "gmpe_reset", "gmpe_step", "gmpe_decode_onehot", "gmpe_launch_count", "gmpe_set_seed",
+    "gmpe_kernel_name",
 )
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -150,6 +151,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.gmpe_decode_onehot.restype = C.c_int
     lib.gmpe_launch_count.argtypes = [C.c_void_p]
     lib.gmpe_launch_count.restype = C.c_int64
+    lib.gmpe_kernel_name.argtypes = [C.c_void_p]
+    lib.gmpe_kernel_name.restype = C.c_char_p
     lib.gmpe_set_seed.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
     lib.gmpe_set_seed.restype = C.c_int
     v = lib.gmpe_abi_version()

@@ -286,6 +286,11 @@ const char* gmpe_last_error(gmpe_handle h) { return h ? h->err.c_str() : g_creat
 
 int64_t gmpe_launch_count(gmpe_handle h) { return h ? h->launches : 0; }
 
+const char* gmpe_kernel_name(gmpe_handle h) {
+  if (!h) return "";
+  return h->small == KERNEL_COOP ? "gmpe_step_coop_kernel" : (h->small == KERNEL_WORLD ? "gmpe_step_small_kernel" : "gmpe_step_kernel");
+}
+
 int gmpe_set_seed(gmpe_handle h, uint64_t seed, int64_t world_offset) {
   if (!h) return GMPE_E_NULL;
   h->cfg.seed = seed;

@@ -92,6 +92,11 @@ class BatchedGraphMPE:
     def launch_count(self) -> int:
         return int(self.lib.gmpe_launch_count(self._h))
 
+    @property
+    def kernel_name(self) -> str:
+        """Which step kernel gmpe_create picked for this configuration."""
+        return self.lib.gmpe_kernel_name(self._h).decode()
+
     def _inject(self, theta_draw, reset_state):
         if theta_draw is None and reset_state is None:
             return self._null_inject, None

@@ -225,7 +225,7 @@ class _BatchedVecEnv(ShareVecEnv):
         else:
             a = np.asarray(actions)
             if a.shape == (B, N) and np.issubdtype(a.dtype, np.integer):  # index fast path
-                self._idx_pin.numpy()[...] = a
+                self._idx_pin.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)))
                 eng.action_idx.copy_(self._idx_pin, non_blocking=True)
                 idx = eng.action_idx
                 self.h2d_bytes_last = self._idx_pin.numel() * 4
@@ -233,7 +233,10 @@ class _BatchedVecEnv(ShareVecEnv):
                 if a.shape != (B, N, A):
                     raise ValueError(f"actions must have shape {(B, N, A)} (one-hot) or {(B, N)} (int), got {a.shape}")
                 w = 8 if a.dtype == np.float64 else 4
-                self._act_pin[w].numpy()[...] = a
+                if a.dtype not in (np.float64, np.float32):
+                    a = a.astype(np.float32)
+                # torch's threaded copy fills the pinned block ~15x faster than a numpy assignment
+                self._act_pin[w].copy_(torch.from_numpy(np.ascontiguousarray(a)))
                 self._act_dev[w].copy_(self._act_pin[w], non_blocking=True)
                 idx = eng.decode_onehot(self._act_dev[w])
                 self.h2d_bytes_last = a.size * w

@@ -9,7 +9,9 @@
  *
  * Conventions
  *   - every buffer is CALLER-OWNED device memory (the Python host passes
- *     torch.Tensor.data_ptr()); the library never allocates outputs;
+ *     torch.Tensor.data_ptr()); the library never allocates outputs (its only own device
+ *     memory is a 256/512-byte action table per handle).  Arrays of Real must be aligned to
+ *     16 bytes, out.node_obs and out.info to 32 bytes (256-bit row stores);
  *   - 0 = ok, negative = error (GMPE_E_*), text via gmpe_last_error();
  *   - asynchronous on the caller's stream, no host synchronisation inside
  *     reset/step; one handle per device, not re-entrant, no internal threads;
@@ -26,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GMPE_ABI_VERSION 3
+#define GMPE_ABI_VERSION 4
 
 /* error codes */
 #define GMPE_OK 0
@@ -257,6 +259,11 @@ int gmpe_set_seed(gmpe_handle h, uint64_t seed, int64_t world_offset);
 
 /* Number of kernel launches issued through this handle so far (bench gpu_launches). */
 int64_t gmpe_launch_count(gmpe_handle h);
+
+/* Name of the step kernel this handle launches (which mapping gmpe_create picked for the
+ * configuration: "gmpe_step_coop_kernel", "gmpe_step_small_kernel" or "gmpe_step_kernel");
+ * bench / profile bookkeeping only. */
+const char* gmpe_kernel_name(gmpe_handle h);
 
 #ifdef __cplusplus
 }
