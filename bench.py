@@ -363,6 +363,10 @@ def main():
         run_reference(opts)
     else:
         run_ours(opts)
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
