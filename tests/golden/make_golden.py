@@ -232,6 +232,64 @@ def run_july_trace(path, seed, T, policy, eps=0.15, episodes=1, **over):
           f"rew[{out['reward'].min():.2f},{out['reward'].max():.2f}] size={os.path.getsize(path)//1024}KB")
 
 
+def run_classic_trace(path, seed, T, num_agents=3, num_landmarks=3, pull=0.8):
+    """Stage-1 FORCE physics oracle: the classic MPE copy whose World.step runs
+    apply_action_force / apply_environment_force / integrate_state live
+    (onpolicy/envs/mpe/core.py:183-335) through onpolicy/envs/mpe/environment.py +
+    scenarios/simple_spread.py.  The trace holds the agent (x, y, vx, vy) trajectory under a
+    seeded action stream in which agents chase their nearest neighbour, so that they actually collide."""
+    import argparse
+    import contextlib
+    import io
+
+    cwd = os.getcwd()
+    os.chdir(REFERENCE_ROOT)
+    try:
+        from onpolicy.envs.mpe.environment import MultiAgentEnv
+        from onpolicy.envs.mpe.scenarios import load
+    finally:
+        os.chdir(cwd)
+    args = argparse.Namespace(num_agents=num_agents, num_landmarks=num_landmarks, episode_length=T, scenario_name="simple_spread")
+    np.random.seed(seed)
+    scenario = load("simple_spread.py").Scenario()
+    world = scenario.make_world(args)
+    env = MultiAgentEnv(world, scenario.reset_world, scenario.reward, scenario.observation, scenario.info)
+    np.random.seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        env.reset()
+    ag = world.agents
+    init_state = np.array([[*a.state.p_pos, *a.state.p_vel] for a in ag])
+    init_lm = np.array([l.state.p_pos.copy() for l in world.landmarks])
+    rs = np.random.RandomState(seed + 100)
+    acts, states, hits = [], [], 0
+    for t in range(T):
+        a_idx = []
+        for a in ag:
+            if rs.rand() < pull:  # chase the nearest other agent; one-hot decode u = [a1 - a2, a3 - a4] (environment.py:238-239)
+                others = [o for o in ag if o is not a]
+                tgt = min(others, key=lambda o: np.linalg.norm(o.state.p_pos - a.state.p_pos))
+                d = tgt.state.p_pos - a.state.p_pos
+                k = (1 if d[0] > 0 else 2) if abs(d[0]) > abs(d[1]) else (3 if d[1] > 0 else 4)
+            else:
+                k = int(rs.randint(5))
+            a_idx.append(k)
+        onehot = [np.eye(5)[k] for k in a_idx]
+        with contextlib.redirect_stdout(io.StringIO()):
+            env.step(onehot)
+        acts.append(a_idx)
+        states.append([[*a.state.p_pos, *a.state.p_vel] for a in ag])
+        for i in range(len(ag)):
+            for j in range(i + 1, len(ag)):
+                hits += int(np.linalg.norm(ag[i].state.p_pos - ag[j].state.p_pos) < ag[i].size + ag[j].size)
+    out = dict(init_agent_state=init_state, init_landmarks=init_lm, actions=np.array(acts, dtype=np.int32),
+               state=np.array(states), T=T, size=float(ag[0].size), dt=float(world.dt), damping=float(world.damping),
+               contact_force=float(world.contact_force), contact_margin=float(world.contact_margin),
+               num_agents=num_agents, num_landmarks=num_landmarks)
+    np.savez_compressed(path, **out)
+    print(f"{os.path.basename(path)}: classic MPE force step N={num_agents} T={T} contact pair-steps={hits} "
+          f"size={os.path.getsize(path)//1024}KB")
+
+
 def main():
     install_shims()
     g = lambda name: os.path.join(HERE, name)
@@ -253,6 +311,9 @@ def main():
     from multiagent.config import UnicycleVehicleConfig
     UnicycleVehicleConfig.COORDINATION_RANGE = UnicycleVehicleConfig.COMMUNICATION_RANGE
     run_july_trace(g("july_n3_unicycle_s9.npz"), seed=9, T=120, policy="pursuit", dynamics_type="unicycle_vehicle")
+    # stage-1 force physics: the live classic-MPE World.step
+    run_classic_trace(g("classic_spread_n3_s11.npz"), seed=11, T=120)
+    run_classic_trace(g("classic_spread_n6_s12.npz"), seed=12, T=80, num_agents=6, num_landmarks=6)
 
 
 if __name__ == "__main__":
