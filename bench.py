@@ -280,6 +280,25 @@ def run_ours(opts):
     copy_gbs = 2 * half / (copy_ms * 1e-3) / 1e9
     del csrc, cdst
 
+    # the rollout glue either side of the path: steps written in place into a
+    # device rollout buffer with the runner's mask bookkeeping, actions as device int32 indices
+    from gmpe_b200.rollout import DeviceGraphRollout
+
+    Tr = args.episode_length
+    roll = DeviceGraphRollout(eng, Tr)
+    roll.warmup()
+    for t in range(min(W, Tr)):
+        roll.insert_env_step(acts[t])
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(stream)
+    for t in range(K):
+        roll.insert_env_step(acts[W + t])
+    r1.record(stream)
+    torch.cuda.synchronize()
+    roll_ms = gdist.max_over_ranks(r0.elapsed_time(r1), dev) / K
+    del roll
+
     # e2e through the reference-facing vec env with host buffers
     eng.close()
     del eng
@@ -323,6 +342,9 @@ def run_ours(opts):
         "env_steps_per_s": value / N,
         "hot_l2": {"ms_per_step": hot_ms, "value": world * Bg * N / (hot_ms * 1e-3),
                    "note": "K steps back to back without the flush (rollout mode)"},
+        "device_rollout": {"ms_per_step": roll_ms, "value": world * Bg * N / (roll_ms * 1e-3),
+                           "note": "DeviceGraphRollout.insert_env_step: step outputs land in slot t+1 of the device "
+                                   "rollout buffer (no copy) + masks / active_masks, K steps back to back"},
         "wall_s_timed_region": t_wall,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name + "<float>",

@@ -111,19 +111,34 @@ class BatchedGraphMPE:
         return buffers.make_inject(theta_draw, reset_state)
 
     # -- hot path ---------------------------------------------------------------------
-    def reset(self, env_mask=None, reset_state: dict | None = None) -> dict:
+    def reset(self, env_mask=None, reset_state: dict | None = None, out_struct=None) -> dict:
         """MultiAgentGraphEnv.reset for every masked world (environment.py:1066-1081)."""
         inj, keep = self._inject(None, reset_state)
         m = None
         if env_mask is not None:
             m = torch.as_tensor(env_mask, device=self.device).to(torch.uint8).contiguous()
         rc = self.lib.gmpe_reset(self._h, C.byref(self._st), m.data_ptr() if m is not None else None,
-                                 C.byref(inj), C.byref(self._out), self._stream())
+                                 C.byref(inj), C.byref(self._out if out_struct is None else out_struct), self._stream())
         self._check(rc, "gmpe_reset")
         self._keep = (keep, m)
         return self.out
 
-    def step(self, action_idx: torch.Tensor, theta_draw=None, reset_state: dict | None = None) -> dict:
+    def redirect(self, **tensors) -> "abi.GmpeStepOut":
+        """A GmpeStepOut that writes the named outputs into caller tensors (same shape / dtype,
+        contiguous, on this device) instead of the engine's arena -- e.g. slot t+1 of a device
+        rollout buffer, so that a step lands where the learner reads it with no copy at all.
+        Pass the result as ``out_struct=`` to :meth:`step` / :meth:`reset`."""
+        merged = dict(self.out)
+        for k, t in tensors.items():
+            ref = self.out[k]
+            if tuple(t.shape) != tuple(ref.shape) or t.dtype != ref.dtype or t.device != ref.device or not t.is_contiguous():
+                raise ValueError(f"redirect({k}): need a contiguous {tuple(ref.shape)} {ref.dtype} tensor on {ref.device}")
+            merged[k] = t
+        s = buffers.make_struct(abi.GmpeStepOut, merged)
+        s._keepalive = merged
+        return s
+
+    def step(self, action_idx: torch.Tensor, theta_draw=None, reset_state: dict | None = None, out_struct=None) -> dict:
         """One env step for the whole batch. ``action_idx``: int32 (B, N) device tensor."""
         if action_idx.dtype != torch.int32 or action_idx.device != self.device or not action_idx.is_contiguous():
             action_idx = action_idx.to(device=self.device, dtype=torch.int32).contiguous()
@@ -131,7 +146,7 @@ class BatchedGraphMPE:
             raise ValueError(f"action_idx must have shape {(self.B, self.N)}, got {tuple(action_idx.shape)}")
         inj, keep = self._inject(theta_draw, reset_state)
         rc = self.lib.gmpe_step(self._h, C.byref(self._st), action_idx.data_ptr(), C.byref(inj),
-                                C.byref(self._out), self._stream())
+                                C.byref(self._out if out_struct is None else out_struct), self._stream())
         self._check(rc, "gmpe_step")
         self._keep = (keep, action_idx)
         return self.out
