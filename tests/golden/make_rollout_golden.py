@@ -86,3 +86,37 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_infos_golden():
+    """Runner.process_infos + log_env (onpolicy/runner/shared/base_runner.py:194-302) executed
+    from their own source text on a seeded synthetic info stream -> tests/golden/process_infos_n3.npz."""
+    import json
+
+    src = open(os.path.join(REFERENCE_ROOT, "onpolicy/runner/shared/base_runner.py")).read()
+    fn = None
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.FunctionDef) and node.name == "process_infos":
+            ns = {"np": np}
+            exec(textwrap.dedent(ast.unparse(node)), ns)
+            fn = ns["process_infos"]
+    from gmpe_b200 import abi
+
+    B, N, T, dt = 11, 3, 200, 1.0
+    rs = np.random.RandomState(9)
+    info = rs.rand(B, N, len(abi.INFO_KEYS)) * 10
+    j = abi.INFO_KEYS.index("Time_req_to_goal")
+    info[..., j] = np.where(rs.rand(B, N) < 0.4, -1.0, np.floor(info[..., j]))
+    rew = rs.randn(B, N)
+    infos = [[dict({"individual_reward": rew[e, a]}, **{k: info[e, a, c] for c, k in enumerate(abi.INFO_KEYS)}) for a in range(N)]
+             for e in range(B)]
+    me = types.SimpleNamespace(num_agents=N, all_args=types.SimpleNamespace(episode_length=T), dt=dt)
+    env_infos = fn(me, infos)
+    logged = {k: float(np.mean(v)) for k, v in env_infos.items() if len(v) > 0}  # log_env, base_runner.py:298-302
+    path = os.path.join(HERE, "process_infos_n3.npz")
+    np.savez_compressed(path, info=info, indiv_reward=rew, episode_length=T, dt=dt, logged_json=json.dumps(logged))
+    print(path, len(logged), "logged keys")
+
+
+if __name__ == "__main__":
+    make_infos_golden()
