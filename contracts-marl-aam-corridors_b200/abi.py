@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # error codes
 OK, E_INVALID, E_CUDA, E_NULL = 0, -1, -2, -3
@@ -97,7 +97,7 @@ class GmpeState(C.Structure):
 class GmpeStepOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "obs", "node_obs", "adj", "reward", "done", "info", "edge_index", "edge_attr", "num_edges",
-        "gnn_edge_index", "gnn_edge_attr", "gnn_num_edges", "indiv_reward")]
+        "gnn_edge_index", "gnn_edge_attr", "gnn_num_edges", "indiv_reward", "mask", "active_mask")]
 
 
 class GmpeStepInject(C.Structure):

@@ -15,6 +15,8 @@ STATE_FIELDS = ("agent_state", "agent_aux", "agent_flags", "agent_cnt", "world_f
                 "landmarks", "obstacles", "walls")
 OUT_FIELDS = ("obs", "node_obs", "adj", "reward", "done", "info", "edge_index", "edge_attr",
               "num_edges", "gnn_edge_index", "gnn_edge_attr", "gnn_num_edges", "indiv_reward")
+#: optional float32 outputs (runner masks); only requested by DeviceGraphRollout
+MASK_FIELDS = ("mask", "active_mask")
 
 
 def shapes(cfg: abi.GmpeConfig) -> dict:
@@ -45,6 +47,8 @@ def shapes(cfg: abi.GmpeConfig) -> dict:
         "gnn_edge_attr": ((B, cap), "real"),
         "gnn_num_edges": ((B,), "i32"),
         "indiv_reward": ((B, N), "real"),
+        "mask": ((B, N), "f32"),
+        "active_mask": ((B, N), "f32"),
     }
 
 
@@ -60,7 +64,7 @@ def wanted_outputs(cfg: abi.GmpeConfig) -> tuple:
 
 
 def alloc_numpy(cfg: abi.GmpeConfig, names, real=np.float64) -> dict:
-    kinds = {"real": real, "i32": np.int32, "u8": np.uint8}
+    kinds = {"real": real, "i32": np.int32, "u8": np.uint8, "f32": np.float32}
     sh = shapes(cfg)
     return {n: np.zeros(sh[n][0], dtype=kinds[sh[n][1]]) for n in names}
 

@@ -398,6 +398,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         ((Real*)p.out.reward)[ga] = collab ? rsum : rew;
         if (p.out.indiv_reward) ((Real*)p.out.indiv_reward)[ga] = rew;
         p.out.done[ga] = (uint8_t)done;
+        if (p.out.mask) p.out.mask[ga] = done ? 0.0f : 1.0f;  // GMPERunner.insert (graph_mpe_runner.py:397-405)
+        if (p.out.active_mask) p.out.active_mask[ga] = (all_done || !done) ? 1.0f : 0.0f;
       }
       rs = valid && (c.flags & GMPE_FLAG_AUTO_RESET) && all_done;
       if (valid && !rs) {

@@ -585,6 +585,8 @@ gmpe_step_small_kernel(const __grid_constant__ KParams p) {
           ((Real*)p.out.reward)[ga0 + i] = collab ? rsum : rew[i];
           if (p.out.indiv_reward) ((Real*)p.out.indiv_reward)[ga0 + i] = rew[i];
           p.out.done[ga0 + i] = (uint8_t)done[i];
+          if (p.out.mask) p.out.mask[ga0 + i] = done[i] ? 0.0f : 1.0f;  // GMPERunner.insert (graph_mpe_runner.py:397-405)
+          if (p.out.active_mask) p.out.active_mask[ga0 + i] = (all_done || !done[i]) ? 1.0f : 0.0f;
         }
       }
       if (do_info && !GMPE_SMALL_DIRECT_ROWS) {

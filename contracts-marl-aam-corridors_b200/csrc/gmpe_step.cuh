@@ -739,6 +739,8 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
       p.out.done[ga] = (uint8_t)done;
       bool all_done = true;
       for (int k = 0; k < N; ++k) all_done = all_done && sm.done[lw * N + k];
+      if (p.out.mask) p.out.mask[ga] = done ? 0.0f : 1.0f;  // GMPERunner.insert (graph_mpe_runner.py:397-405)
+      if (p.out.active_mask) p.out.active_mask[ga] = (all_done || !done) ? 1.0f : 0.0f;
       if (do_info) {
         // world-level statistics are recomputed inside every agent's info_callback while
         // later agents still hold last step's values (july:789-793, 800-823)

@@ -129,10 +129,12 @@ class BatchedGraphMPE:
         rollout buffer, so that a step lands where the learner reads it with no copy at all.
         Pass the result as ``out_struct=`` to :meth:`step` / :meth:`reset`."""
         merged = dict(self.out)
+        sh = buffers.shapes(self.cfg)
+        kinds = {"real": self.real, "i32": torch.int32, "u8": torch.uint8, "f32": torch.float32}
         for k, t in tensors.items():
-            ref = self.out[k]
-            if tuple(t.shape) != tuple(ref.shape) or t.dtype != ref.dtype or t.device != ref.device or not t.is_contiguous():
-                raise ValueError(f"redirect({k}): need a contiguous {tuple(ref.shape)} {ref.dtype} tensor on {ref.device}")
+            shape, dtype = tuple(sh[k][0]), kinds[sh[k][1]]
+            if tuple(t.shape) != shape or t.dtype != dtype or t.device != self.device or not t.is_contiguous():
+                raise ValueError(f"redirect({k}): need a contiguous {shape} {dtype} tensor on {self.device}")
             merged[k] = t
         s = buffers.make_struct(abi.GmpeStepOut, merged)
         s._keepalive = merged

@@ -8,8 +8,8 @@ onpolicy/envs/env_wrappers.py:996-1004, onpolicy/runner/shared/graph_mpe_runner.
 onpolicy/utils/graph_buffer.py:168-252, graph_mpe_runner.py:343-356).  Here the step kernel
 writes obs / node_obs / adj / reward / done **directly into slot t+1** of device tensors that
 have the buffer's layout (the C ABI takes output pointers, so this is a pointer swap, not a
-copy), and the runner's mask bookkeeping is a few fused element-wise torch ops on (B, N, 1)
-tensors.
+copy), and the runner's mask bookkeeping (masks / active_masks) comes out of the same kernel,
+so one launch is all a rollout step costs.
 
 Fields mirror ``GraphReplayBuffer`` (graph_buffer.py:84-165), env-produced ones only:
 ``obs, share_obs, node_obs, adj, agent_id, share_agent_id, rewards, masks, active_masks,
@@ -50,8 +50,10 @@ class DeviceGraphRollout:
         ids = torch.arange(N, dtype=torch.int32, device=dev)
         self.agent_id = ids.view(1, 1, N, 1).expand(T1, B, N, 1)
         self.share_agent_id = (ids.view(1, 1, 1, N).expand(T1, B, N, N) if use_centralized_V else self.agent_id)
+        # masks / active_masks are written by the step kernel too (GmpeStepOut.mask / active_mask)
         self._structs = [engine.redirect(obs=self._obs[t + 1], node_obs=self._node_obs[t + 1], adj=self._adj[t + 1],
-                                         reward=self._reward[t], done=self._done[t]) for t in range(self.T)]
+                                         reward=self._reward[t], done=self._done[t], mask=self.masks[t + 1].view(B, N),
+                                         active_mask=self.active_masks[t + 1].view(B, N)) for t in range(self.T)]
         self._reset_struct = engine.redirect(obs=self._obs[0], node_obs=self._node_obs[0], adj=self._adj[0])
         self.step = 0
 
@@ -97,14 +99,9 @@ class DeviceGraphRollout:
         ``action_idx``: int32 (B, N) on the device (the runner's argmax'd actions)."""
         t = self.step
         self.engine.step(action_idx, out_struct=self._structs[t])
-        dones = self._done[t] != 0
-        alive = (~dones).to(torch.float32).unsqueeze(-1)
-        self.masks[t + 1] = alive                                      # masks[dones] = 0
-        dones_env = dones.all(dim=1).view(-1, 1, 1)                    # np.all(dones, axis=1)
-        self.active_masks[t + 1] = torch.where(dones_env, torch.ones_like(alive), alive)
         self.step = (t + 1) % self.T
         return self._obs[t + 1], self.agent_id[t + 1], self._node_obs[t + 1], self.adj[t + 1], \
-            self.rewards[t], dones
+            self.rewards[t], self._done[t]
 
     def after_update(self):
         """GraphReplayBuffer.after_update (graph_buffer.py:254-287): last slot -> slot 0."""

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GMPE_ABI_VERSION 4
+#define GMPE_ABI_VERSION 5
 
 /* error codes */
 #define GMPE_OK 0
@@ -205,6 +205,11 @@ typedef struct GmpeStepOut {
   int32_t* gnn_num_edges;  /* i32 [B]                                                                   */
   void* indiv_reward;      /* Real [B][N] reward before the collaborative sum: info['individual_reward']
                                           (environment.py:1050)                                          */
+  float* mask;             /* f32 [B][N] GMPERunner.insert masks: 0 where done, else 1
+                                          (onpolicy/runner/shared/graph_mpe_runner.py:397-402)           */
+  float* active_mask;      /* f32 [B][N] ... active_masks: like mask, but 1 for every agent of a world
+                                          whose agents are all done (graph_mpe_runner.py:403-405); both
+                                          are float32 like the reference buffer, written by gmpe_step only */
 } GmpeStepOut;
 
 /* Teacher forcing for bit-parity runs.  NULL pointers = on-device Philox. */

@@ -920,6 +920,12 @@ static void step_world(World* w, const int32_t* act, const GmpeStepInject* inj, 
     for (int i = 0; i < N; ++i) r[i] = sum;
   } else for (int i = 0; i < N; ++i) r[i] = rew[i];
   if (out->indiv_reward) for (int i = 0; i < N; ++i) ((double*)out->indiv_reward)[w->b * N + i] = rew[i]; /* env:1050 */
+  /* GMPERunner.insert masks / active_masks (onpolicy/runner/shared/graph_mpe_runner.py:397-405) */
+  for (int i = 0; i < N; ++i) {
+    int d = out->done[w->b * N + i] != 0;
+    if (out->mask) out->mask[w->b * N + i] = d ? 0.0f : 1.0f;
+    if (out->active_mask) out->active_mask[w->b * N + i] = (all_done || !d) ? 1.0f : 0.0f;
+  }
   write_graph_outputs(w, out);
   if ((c->flags & GMPE_FLAG_AUTO_RESET) && all_done) reset_world(w, inj, out); /* wrap:869-870 */
 }
