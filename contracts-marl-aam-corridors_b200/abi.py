@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # error codes
 OK, E_INVALID, E_CUDA, E_NULL = 0, -1, -2, -3
@@ -108,7 +108,7 @@ class GmpeStepInject(C.Structure):
 EXPORTED_SYMBOLS = (
     "gmpe_abi_version", "gmpe_create", "gmpe_destroy", "gmpe_last_error", "gmpe_layout",
     "gmpe_reset", "gmpe_step", "gmpe_decode_onehot", "gmpe_launch_count", "gmpe_set_seed",
-    "gmpe_kernel_name",
+    "gmpe_kernel_name", "gmpe_step_range", "gmpe_decode_onehot_range",
 )
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -149,6 +149,11 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.gmpe_step.restype = C.c_int
     lib.gmpe_decode_onehot.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.gmpe_decode_onehot.restype = C.c_int
+    lib.gmpe_step_range.argtypes = [C.c_void_p, C.POINTER(GmpeState), C.c_void_p, C.POINTER(GmpeStepInject),
+                                    C.POINTER(GmpeStepOut), C.c_int64, C.c_int64, C.c_void_p]
+    lib.gmpe_step_range.restype = C.c_int
+    lib.gmpe_decode_onehot_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    lib.gmpe_decode_onehot_range.restype = C.c_int
     lib.gmpe_launch_count.argtypes = [C.c_void_p]
     lib.gmpe_launch_count.restype = C.c_int64
     lib.gmpe_kernel_name.argtypes = [C.c_void_p]

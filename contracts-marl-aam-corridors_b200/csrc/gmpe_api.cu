@@ -25,6 +25,7 @@ struct gmpe_ctx {
   int stage_graph;
   int small;  // KERNEL_TILE (gmpe_step.cuh) / KERNEL_WORLD (gmpe_small.cuh) / KERNEL_COOP (gmpe_coop.cuh)
   const void* fn;
+  int64_t resident;  // CTAs of the step kernel that fit on the device at once
   void* act_tab;  // device copy of the _set_action table (Real [32][2]); the only memory the library owns
   int64_t launches;
   std::string err;
@@ -110,6 +111,58 @@ static int pick_kernel(const GmpeConfig& c) {
     if (!strcmp(k, "world")) return KERNEL_WORLD;
   }
   return KERNEL_COOP;
+}
+
+// Persistent grid: at most one wave of resident CTAs, units strided over it.  When the batch
+// needs r > 1 rounds the grid is shrunk to ceil(units / r) CTAs so that every CTA runs exactly
+// r rounds (a last round that only a few CTAs take part in leaves the SMs idle).
+static int grid_for(const gmpe_ctx* h, int64_t units) {
+  const int64_t g = h->resident;
+  bool persistent = true;
+  if (const char* t = getenv("GMPE_PERSISTENT")) persistent = atoi(t) != 0;  // tuning knob (tools/ab.py)
+  if (units <= g || !persistent) return (int)units;
+  const int64_t rounds = (units + g - 1) / g;
+  if (const char* t = getenv("GMPE_BALANCED")) if (!atoi(t)) return (int)g;
+  return (int)((units + rounds - 1) / rounds);
+}
+
+template <typename T>
+static void shift(T*& ptr, int64_t elems) { if (ptr) ptr += elems; }
+static void shift_bytes(void*& ptr, int64_t bytes) { if (ptr) ptr = (char*)ptr + bytes; }
+static void shift_bytes(const void*& ptr, int64_t bytes) { if (ptr) ptr = (const char*)ptr + bytes; }
+
+// Re-base every world-major array on world `b0` (gmpe_step_range / gmpe_reset_range).
+static void rebase_state(GmpeState& s, const GmpeConfig& c, int64_t b0, int64_t R) {
+  const int64_t N = c.num_agents;
+  shift_bytes(s.agent_state, b0 * N * 4 * R);
+  shift_bytes(s.agent_aux, b0 * N * 2 * R);
+  shift(s.agent_flags, b0 * N * 4);
+  shift(s.agent_cnt, b0 * N * GMPE_AGENT_CNT);
+  shift_bytes(s.world_f, b0 * GMPE_WORLD_F * R);
+  shift(s.world_i, b0 * GMPE_WORLD_I);
+  shift_bytes(s.landmarks, b0 * c.num_landmarks * 2 * R);
+  shift_bytes(s.obstacles, b0 * c.num_obstacles * 2 * R);
+  shift_bytes(s.walls, b0 * c.num_walls * GMPE_WALL_F * R);
+}
+
+static void rebase_out(GmpeStepOut& o, const GmpeConfig& c, int64_t b0, int64_t R) {
+  const int64_t N = c.num_agents, E = N + c.num_landmarks + c.num_obstacles + c.num_walls, cap = E * (E - 1);
+  const int64_t F = c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
+  shift_bytes(o.obs, b0 * N * F * R);
+  shift_bytes(o.node_obs, b0 * N * E * 8 * R);
+  shift_bytes(o.adj, b0 * E * E * R);
+  shift_bytes(o.reward, b0 * N * R);
+  shift(o.done, b0 * N);
+  shift_bytes(o.info, b0 * N * GMPE_INFO_K * R);
+  shift(o.edge_index, b0 * 2 * cap);
+  shift_bytes(o.edge_attr, b0 * cap * R);
+  shift(o.num_edges, b0);
+  shift(o.gnn_edge_index, b0 * 2 * cap);
+  shift_bytes(o.gnn_edge_attr, b0 * cap * R);
+  shift(o.gnn_num_edges, b0);
+  shift_bytes(o.indiv_reward, b0 * N * R);
+  shift(o.mask, b0 * N);
+  shift(o.active_mask, b0 * N);
 }
 
 extern "C" {
@@ -250,20 +303,8 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
   }
   // persistent grid: one wave of resident CTAs, tiles strided over it (148 SMs on B200)
   int64_t g = (int64_t)h->sm_count * per_sm;
-  // tile / thread-per-world kernels: persistent grid, one wave of resident CTAs strided over the
-  // batch; lane-per-agent kernel: one warp per group of worlds, balanced by the block scheduler
-  // Persistent grid: at most one wave of resident CTAs, units strided over it.  When the batch
-  // needs r > 1 rounds the grid is shrunk to ceil(units / r) CTAs so that every CTA runs exactly
-  // r rounds (a last round that only a few CTAs take part in leaves the SMs idle).
-  bool persistent = true;
-  if (const char* t = getenv("GMPE_PERSISTENT")) persistent = atoi(t) != 0;  // tuning knob (tools/ab.py)
-  if (units <= g || !persistent) {
-    h->grid = units;
-  } else {
-    const int64_t rounds = (units + g - 1) / g;
-    h->grid = (int)((units + rounds - 1) / rounds);
-    if (const char* t = getenv("GMPE_BALANCED")) if (!atoi(t)) h->grid = (int)g;
-  }
+  h->resident = g;
+  h->grid = grid_for(h, units);
   cudaSetDevice(prev);
   *out = h;
   return GMPE_OK;
@@ -299,8 +340,10 @@ int gmpe_set_seed(gmpe_handle h, uint64_t seed, int64_t world_offset) {
 }
 
 static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* act, const uint8_t* mask,
-                  const GmpeStepInject* inj, const GmpeStepOut* out, void* stream) {
+                  const GmpeStepInject* inj, const GmpeStepOut* out, void* stream, int64_t b0 = 0, int64_t count = -1) {
   const GmpeConfig& c = h->cfg;
+  if (count < 0) count = c.num_worlds;
+  if (b0 < 0 || count < 1 || b0 + count > c.num_worlds) return fail(h, GMPE_E_INVALID, "world range outside [0, num_worlds)");
   if (!st || !out) return fail(h, GMPE_E_NULL, "state / out struct is NULL");
   if (!st->agent_state || !st->agent_aux || !st->agent_flags || !st->agent_cnt || !st->world_f || !st->world_i || !st->landmarks)
     return fail(h, GMPE_E_NULL, "a required state array is NULL");
@@ -325,6 +368,20 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   p.mode = mode;
   p.wpb = h->wpb;
   p.num_tiles = h->num_tiles;
+  int grid = h->grid;
+  if (b0 != 0 || count != c.num_worlds) {  // a slice of the batch: same arrays, re-based on world b0
+    const int64_t R = c.precision == GMPE_F64 ? 8 : 4;
+    rebase_state(p.st, c, b0, R);
+    rebase_out(p.out, c, b0, R);
+    if (p.has_rst) rebase_state(p.rst, c, b0, R);
+    shift(p.act, b0 * c.num_agents);
+    shift(p.env_mask, b0);
+    shift_bytes(p.theta, b0 * c.num_agents * R);
+    p.c.num_worlds = (int32_t)count;
+    p.c.world_offset += b0;  // Philox streams are keyed by the global world id
+    p.num_tiles = (int)((count + h->wpb - 1) / h->wpb);
+    grid = grid_for(h, p.num_tiles);
+  }
   p.stage_graph = h->stage_graph;
   const int N = c.num_agents, L = c.num_landmarks, O = c.num_obstacles, W = c.num_walls;
   p.E = N + L + O + W;
@@ -341,7 +398,7 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   if (prev != h->device) cudaSetDevice(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   void* kargs[1] = {(void*)&p};
-  cudaError_t e = cudaLaunchKernel(h->fn, dim3(h->grid), dim3(h->threads), kargs, h->smem_bytes, s);
+  cudaError_t e = cudaLaunchKernel(h->fn, dim3(grid), dim3(h->threads), kargs, h->smem_bytes, s);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (prev != h->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e));
@@ -361,12 +418,28 @@ int gmpe_step(gmpe_handle h, const GmpeState* st, const int32_t* action_idx, con
   return launch(h, MODE_STEP, st, action_idx, nullptr, inject, out, cuda_stream);
 }
 
+int gmpe_step_range(gmpe_handle h, const GmpeState* st, const int32_t* action_idx, const GmpeStepInject* inject,
+                    const GmpeStepOut* out, int64_t world_begin, int64_t world_count, void* cuda_stream) {
+  if (!h) return GMPE_E_NULL;
+  return launch(h, MODE_STEP, st, action_idx, nullptr, inject, out, cuda_stream, world_begin, world_count);
+}
+
 int gmpe_decode_onehot(gmpe_handle h, const void* onehot, int elem_bytes, int32_t* action_idx, void* cuda_stream) {
+  if (!h) return GMPE_E_NULL;
+  return gmpe_decode_onehot_range(h, onehot, elem_bytes, action_idx, 0, h->cfg.num_worlds, cuda_stream);
+}
+
+int gmpe_decode_onehot_range(gmpe_handle h, const void* onehot, int elem_bytes, int32_t* action_idx, int64_t world_begin,
+                             int64_t world_count, void* cuda_stream) {
   if (!h) return GMPE_E_NULL;
   if (!onehot || !action_idx) return fail(h, GMPE_E_NULL, "gmpe_decode_onehot: NULL buffer");
   if (elem_bytes != 4 && elem_bytes != 8) return fail(h, GMPE_E_INVALID, "gmpe_decode_onehot: elem_bytes must be 4 or 8");
-  const int64_t rows = (int64_t)h->cfg.num_worlds * h->cfg.num_agents;
+  if (world_begin < 0 || world_count < 1 || world_begin + world_count > h->cfg.num_worlds)
+    return fail(h, GMPE_E_INVALID, "world range outside [0, num_worlds)");
+  const int64_t rows = world_count * h->cfg.num_agents;
   const int A = h->cfg.total_actions;
+  onehot = (const char*)onehot + world_begin * h->cfg.num_agents * A * elem_bytes;
+  action_idx += world_begin * h->cfg.num_agents;
   int prev = 0;
   cudaGetDevice(&prev);
   if (prev != h->device) cudaSetDevice(h->device);

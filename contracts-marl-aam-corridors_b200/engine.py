@@ -153,6 +153,20 @@ class BatchedGraphMPE:
         self._keep = (keep, action_idx)
         return self.out
 
+    def step_range(self, action_idx: torch.Tensor, begin: int, count: int, stream: torch.cuda.Stream | None = None,
+                   onehot: torch.Tensor | None = None) -> None:
+        """The step for worlds ``[begin, begin + count)`` on ``stream`` (whole-batch tensors;
+        ``onehot`` -- the (B, N, A) device block of the runner's one-hot actions -- is decoded
+        into ``action_idx`` first when given).  Slices are independent: see gmpe_step_range."""
+        s = C.c_void_p((stream or torch.cuda.current_stream(self.device)).cuda_stream)
+        if onehot is not None:
+            rc = self.lib.gmpe_decode_onehot_range(self._h, onehot.data_ptr(), onehot.element_size(), action_idx.data_ptr(),
+                                                   begin, count, s)
+            self._check(rc, "gmpe_decode_onehot_range")
+        rc = self.lib.gmpe_step_range(self._h, C.byref(self._st), action_idx.data_ptr(), C.byref(self._null_inject),
+                                      C.byref(self._out), begin, count, s)
+        self._check(rc, "gmpe_step_range")
+
     def decode_onehot(self, onehot: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """argmax of the runner's one-hot actions (environment.py:431,444) on device."""
         A = self.cfg.total_actions

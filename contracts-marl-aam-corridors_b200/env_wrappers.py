@@ -111,10 +111,31 @@ class _AgentInfo:
 
 class LazyInfos:
     """``infos[env][agent][key]`` as GMPERunner.process_infos walks it
-    (onpolicy/runner/shared/base_runner.py:194-284) without building B*N python dicts."""
+    (onpolicy/runner/shared/base_runner.py:194-284) without building B*N python dicts.
 
-    def __init__(self, info: np.ndarray, indiv_reward: np.ndarray):
-        self.info, self.rew = info, indiv_reward
+    With ``fetch`` the info rows are still on the GPU: the runner reads infos only when it logs
+    (graph_mpe_runner.py:179-195), so the 20 % of a step's device->host bytes they account for
+    are copied on first access instead of every step.  They must be read before the env steps
+    again (the device rows are overwritten); a later access raises instead of returning the
+    wrong step's values."""
+
+    def __init__(self, info: np.ndarray = None, indiv_reward: np.ndarray = None, fetch=None):
+        self._info, self._rew, self._fetch = info, indiv_reward, fetch
+
+    def _load(self):
+        if self._info is None:
+            self._info, self._rew = self._fetch()
+            self._fetch = None
+
+    @property
+    def info(self) -> np.ndarray:
+        self._load()
+        return self._info
+
+    @property
+    def rew(self) -> np.ndarray:
+        self._load()
+        return self._rew
 
     def __len__(self):
         return self.info.shape[0]
@@ -134,7 +155,8 @@ class _BatchedVecEnv(ShareVecEnv):
     returns_reset_count = False
 
     def __init__(self, env_fns=None, spaces=None, *, args=None, num_envs=None, device=0, precision="fp32",
-                 seed=None, world_offset=0, output="numpy", info=True, env_edges=False, gnn_edges=False):
+                 seed=None, world_offset=0, output="numpy", info=True, env_edges=False, gnn_edges=False,
+                 pipeline_chunks=None, lazy_info=True):
         if args is None:
             if not env_fns:
                 raise ValueError("need env_fns (reference calling convention) or args=/num_envs=")
@@ -171,10 +193,27 @@ class _BatchedVecEnv(ShareVecEnv):
                          8: torch.empty((B, N, A), dtype=torch.float64, device=dev)}
         self._idx_pin = torch.empty((B, N), dtype=torch.int32).pin_memory()
         nbytes = self.engine.host_prefix_bytes
+        slabs = self.engine.out_slabs
+        self._lazy_info = bool(lazy_info) and output == "numpy" and "info" in slabs
+        #: bytes of the arena a step always brings to the host (obs, node_obs, adj, reward, done)
+        self._core_bytes = slabs["done"][0] + slabs["done"][1] if self._lazy_info else nbytes
+        self._gen = 0
         self._arena = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
         self._flip = 0
         self.h2d_bytes_last = 0
         self.d2h_bytes_last = nbytes
+        # Host-facing steps are PCIe-bound (one-hot block in, every tensor out).  Worlds are
+        # independent, so the batch is stepped in slices (gmpe_step_range): slice k's device->host
+        # copies run on their own stream while slice k+1's host->device copy and kernel proceed.
+        if pipeline_chunks is None:
+            pipeline_chunks = 4 if (output == "numpy" and B >= 8192) else 1
+        self._chunks = max(1, int(pipeline_chunks))
+        self._s_in = torch.cuda.Stream(device=dev)
+        self._s_out = torch.cuda.Stream(device=dev)
+        self._host_names = [n for n in ("obs", "node_obs", "adj", "reward", "done", "indiv_reward", "info")
+                            if n in self.engine.out_slabs and not (self._lazy_info and n in ("indiv_reward", "info"))]
+        self._host_t = [self._host_tensors(a) for a in self._arena]
+        self._pending = None
 
     # -- host views of the pinned arena ---------------------------------------------------
     def _host_views(self, arena: torch.Tensor) -> dict:
@@ -189,14 +228,76 @@ class _BatchedVecEnv(ShareVecEnv):
                 out[n] = np_arena[off:off + nb].view(kinds[n]).reshape(tuple(eng.out[n].shape))
         return out
 
+    def _host_tensors(self, arena: torch.Tensor) -> dict:
+        """torch views of a pinned arena, one per host-visible output (same offsets as the device arena)."""
+        eng = self.engine
+        out = {}
+        for n in self._host_names:
+            off, nb = eng.out_slabs[n]
+            ref = eng.out[n]
+            out[n] = arena[off:off + nb].view(ref.dtype).view(ref.shape)
+        return out
+
+    def _bounds(self):
+        B, k = self.num_envs, self._chunks
+        step = -(-B // k)
+        step = -(-step // 64) * 64  # slices start on multiples of 64 worlds: every slab stays 16-byte aligned
+        return [(b0, min(B, b0 + step)) for b0 in range(0, B, step)]
+
+    def _step_pipelined(self, pinned_actions: torch.Tensor, dev_actions: torch.Tensor, onehot: bool):
+        eng = self.engine
+        cur = torch.cuda.current_stream(eng.device)
+        self._s_in.wait_stream(cur)
+        host = self._host_t[self._flip]
+        arena = self._arena[self._flip]
+        self._flip ^= 1
+        for b0, b1 in self._bounds():
+            with torch.cuda.stream(self._s_in):
+                dev_actions[b0:b1].copy_(pinned_actions[b0:b1], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self._s_in)
+            cur.wait_event(ev_in)
+            eng.step_range(eng.action_idx if onehot else dev_actions, b0, b1 - b0, stream=cur,
+                           onehot=dev_actions if onehot else None)
+            ev_k = torch.cuda.Event()
+            ev_k.record(cur)
+            self._s_out.wait_event(ev_k)
+            with torch.cuda.stream(self._s_out):
+                for n in self._host_names:
+                    host[n][b0:b1].copy_(eng.out[n][b0:b1], non_blocking=True)
+        self._pending = arena
+
     def _fetch(self):
         if self.output == "torch":
             return dict(self.engine.out)
+        if self._pending is not None:  # a pipelined step already has its copies in flight
+            arena, self._pending = self._pending, None
+            self._s_out.synchronize()
+            self._last_arena = arena
+            return self._host_views(arena)
         arena = self._arena[self._flip]
         self._flip ^= 1
-        arena.copy_(self.engine.out_arena[:arena.numel()], non_blocking=True)
+        n = self._core_bytes
+        arena[:n].copy_(self.engine.out_arena[:n], non_blocking=True)
         torch.cuda.current_stream(self.engine.device).synchronize()
+        self._last_arena = arena
         return self._host_views(arena)
+
+    def _info_fetcher(self, arena: torch.Tensor):
+        """Deferred device->host copy of this step's info rows (LazyInfos)."""
+        gen, eng = self._gen, self.engine
+
+        def fetch():
+            if gen != self._gen:
+                raise RuntimeError("infos of an earlier step were read after the env stepped again; read them before "
+                                   "the next step() or construct the vec env with lazy_info=False")
+            lo, hi = self._core_bytes, arena.numel()
+            arena[lo:hi].copy_(eng.out_arena[lo:hi], non_blocking=True)
+            torch.cuda.current_stream(eng.device).synchronize()
+            self.d2h_bytes_last += hi - lo
+            v = self._host_views(arena)
+            return v["info"], v["indiv_reward"]
+        return fetch
 
     def _pack_obs(self, o):
         B, N, E = self.num_envs, self.num_agents, self.engine.E
@@ -214,6 +315,8 @@ class _BatchedVecEnv(ShareVecEnv):
 
     def step_async(self, actions, num_current_episode=None):
         eng = self.engine
+        self._gen += 1
+        self.d2h_bytes_last = self._core_bytes
         B, N, A = self.num_envs, self.num_agents, self._A
         if isinstance(actions, torch.Tensor) and actions.is_cuda:
             if actions.dtype in (torch.int32, torch.int64) and tuple(actions.shape) == (B, N):
@@ -226,9 +329,9 @@ class _BatchedVecEnv(ShareVecEnv):
             a = np.asarray(actions)
             if a.shape == (B, N) and np.issubdtype(a.dtype, np.integer):  # index fast path
                 self._idx_pin.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)))
+                self.h2d_bytes_last = self._idx_pin.numel() * 4
                 eng.action_idx.copy_(self._idx_pin, non_blocking=True)
                 idx = eng.action_idx
-                self.h2d_bytes_last = self._idx_pin.numel() * 4
             else:
                 if a.shape != (B, N, A):
                     raise ValueError(f"actions must have shape {(B, N, A)} (one-hot) or {(B, N)} (int), got {a.shape}")
@@ -237,9 +340,13 @@ class _BatchedVecEnv(ShareVecEnv):
                     a = a.astype(np.float32)
                 # torch's threaded copy fills the pinned block ~15x faster than a numpy assignment
                 self._act_pin[w].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+                self.h2d_bytes_last = a.size * w
+                if self._chunks > 1:
+                    self._step_pipelined(self._act_pin[w], self._act_dev[w], onehot=True)
+                    self.waiting = True
+                    return
                 self._act_dev[w].copy_(self._act_pin[w], non_blocking=True)
                 idx = eng.decode_onehot(self._act_dev[w])
-                self.h2d_bytes_last = a.size * w
         eng.step(idx)
         self.waiting = True
 
@@ -257,7 +364,10 @@ class _BatchedVecEnv(ShareVecEnv):
         else:
             rews = o["reward"][..., None] if collab else o["reward"]  # [[sum]]*N -> (B,N,1), environment.py:1059
             dones = o["done"].view(np.bool_)
-            infos = LazyInfos(o["info"], o["indiv_reward"]) if "info" in o else tuple([{}] * 0)
+            if self._lazy_info:
+                infos = LazyInfos(fetch=self._info_fetcher(self._last_arena))
+            else:
+                infos = LazyInfos(o["info"], o["indiv_reward"]) if "info" in o else tuple([{}] * 0)
         if self.returns_reset_count:
             # env_wrappers.py:925-936: reset_count = 1 when any env auto-reset this step
             if self.output == "torch":

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GMPE_ABI_VERSION 5
+#define GMPE_ABI_VERSION 6
 
 /* error codes */
 #define GMPE_OK 0
@@ -252,11 +252,23 @@ int gmpe_reset(gmpe_handle h, const GmpeState* st, const uint8_t* env_mask,
 int gmpe_step(gmpe_handle h, const GmpeState* st, const int32_t* action_idx,
               const GmpeStepInject* inject, const GmpeStepOut* out, void* cuda_stream);
 
+/* gmpe_step for the worlds [world_begin, world_begin + world_count) only.  All pointers are
+ * the SAME whole-batch arrays gmpe_step takes; the library re-bases them.  Worlds are
+ * independent (graphworker processes in the reference, env_wrappers.py:851-901), so a host can
+ * issue slices on different streams and overlap one slice's device->host copies with the
+ * next slice's host->device copy and kernel (env_wrappers.py here does). */
+int gmpe_step_range(gmpe_handle h, const GmpeState* st, const int32_t* action_idx,
+                    const GmpeStepInject* inject, const GmpeStepOut* out, int64_t world_begin,
+                    int64_t world_count, void* cuda_stream);
+
 /* Front half of _set_action (environment.py:431,444: np.argmax of the one-hot the
  * runner builds with np.eye(A)[a], graph_mpe_runner.py:375-377).
  * onehot: [B][N][A] of float (elem_bytes 4) or double (8); first maximum wins. */
 int gmpe_decode_onehot(gmpe_handle h, const void* onehot, int elem_bytes,
                        int32_t* action_idx, void* cuda_stream);
+/* ... for a slice of worlds (whole-batch pointers, as gmpe_step_range). */
+int gmpe_decode_onehot_range(gmpe_handle h, const void* onehot, int elem_bytes, int32_t* action_idx,
+                             int64_t world_begin, int64_t world_count, void* cuda_stream);
 
 /* Re-key the Philox streams: replaces env.seed(seed) (environment.py:219-223, called by
  * train_mpe.py:31 with seed + rank*1000); world_offset as in GmpeConfig. */

@@ -146,3 +146,63 @@ def test_multi_agent_graph_env_replays_a_golden_episode_through_the_scenario_api
     with pytest.raises(AssertionError):
         env.step([np.eye(24)[0]] * 3)
     env.close()
+
+
+@pytest.mark.parametrize("scen", ["nav", "july"])
+def test_sliced_pipelined_step_equals_the_whole_batch_step(scen):
+    """gmpe_step_range / gmpe_decode_onehot_range: stepping the batch in slices on several
+    streams (what the host-facing vec env does to overlap PCIe copies) is bit-identical to one
+    whole-batch launch, through auto-resets."""
+    from gmpe_b200 import default_args
+    from gmpe_b200.env_wrappers import GraphSubprocVecEnv
+
+    if scen == "nav":
+        args = default_args(scenario_name="navigation_graph", episode_length=5, collaborative=True)
+    else:
+        args = default_args(scenario_name="nav_metered_one_goal_graph_rotate_tube_july", dynamics_type="air_taxi",
+                            world_size=3, episode_length=6, goal_rew=30, collaborative=False)
+    B = 9001  # not a multiple of the slice size
+    a = GraphSubprocVecEnv(args=args, num_envs=B, device=0, seed=4, pipeline_chunks=1)
+    b = GraphSubprocVecEnv(args=args, num_envs=B, device=0, seed=4, pipeline_chunks=5)
+    assert len(b._bounds()) > 1
+    ra, rb = a.reset(), b.reset()
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x, y)
+    A = a.cfg.total_actions
+    rs = np.random.RandomState(1)
+    for t in range(9):
+        idx = rs.randint(A, size=(B, a.num_agents))
+        act = np.eye(A)[idx] if t % 2 == 0 else idx.astype(np.int64)
+        oa, ob = a.step(act, 0), b.step(act, 0)
+        for k in range(6):
+            assert np.array_equal(np.asarray(oa[k]), np.asarray(ob[k]), equal_nan=True), (t, k)
+        assert np.array_equal(oa[6].info, ob[6].info, equal_nan=True) and np.array_equal(oa[6].rew, ob[6].rew)
+    a.close()
+    b.close()
+
+
+def test_lazy_infos_are_fetched_on_access_and_guard_against_stale_reads():
+    from gmpe_b200 import default_args
+    from gmpe_b200.env_wrappers import GraphSubprocVecEnv
+
+    args = default_args(scenario_name="nav_metered_one_goal_graph_rotate_tube_july", dynamics_type="air_taxi",
+                        world_size=3, episode_length=20, goal_rew=30, collaborative=False)
+    lazy = GraphSubprocVecEnv(args=args, num_envs=300, device=0, seed=4)
+    eager = GraphSubprocVecEnv(args=args, num_envs=300, device=0, seed=4, lazy_info=False)
+    lazy.reset(), eager.reset()
+    rs = np.random.RandomState(2)
+    first = None
+    for t in range(5):
+        act = np.eye(25)[rs.randint(25, size=(300, 3))]
+        ol, oe = lazy.step(act, 0), eager.step(act, 0)
+        before = lazy.d2h_bytes_last
+        assert before < eager.d2h_bytes_last
+        assert ol[6][7][1]["Dist_to_goal"] == oe[6][7][1]["Dist_to_goal"]      # the runner's access pattern
+        assert np.array_equal(ol[6].info, oe[6].info, equal_nan=True) and np.array_equal(ol[6].rew, oe[6].rew)
+        assert lazy.d2h_bytes_last == eager.d2h_bytes_last > before           # the info rows came over on access
+        if first is None:
+            first = lazy.step(act, 0)[6]  # never read ...
+            eager.step(act, 0)
+    with pytest.raises(RuntimeError, match="earlier step"):
+        first[0][0]["Dist_to_goal"]       # ... and stale by now
+    lazy.close(), eager.close()
