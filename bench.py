@@ -284,7 +284,8 @@ def run_ours(opts):
     # device rollout buffer with the runner's mask bookkeeping, actions as device int32 indices
     from gmpe_b200.rollout import DeviceGraphRollout
 
-    Tr = args.episode_length
+    slot_bytes = 4 * Bg * (N * eng.layout.obs_dim + N * eng.E * 8 + eng.E * eng.E + 4 * N)
+    Tr = int(min(args.episode_length, max(2, (4 << 30) // slot_bytes)))  # rollout depth bounded to ~4 GiB of HBM
     roll = DeviceGraphRollout(eng, Tr)
     roll.warmup()
     for t in range(min(W, Tr)):
@@ -347,6 +348,7 @@ def run_ours(opts):
         "hot_l2": {"ms_per_step": hot_ms, "value": world * Bg * N / (hot_ms * 1e-3),
                    "note": "K steps back to back without the flush (rollout mode)"},
         "device_rollout": {"ms_per_step": roll_ms, "value": world * Bg * N / (roll_ms * 1e-3),
+                           "rollout_steps": Tr,
                            "note": "DeviceGraphRollout.insert_env_step: step outputs land in slot t+1 of the device "
                                    "rollout buffer (no copy) + masks / active_masks, K steps back to back"},
         "wall_s_timed_region": t_wall,

@@ -70,7 +70,7 @@ __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
 // (BASELINE.json north_star); the fp64 strict-parity instantiation stays IEEE throughout.
 __device__ __forceinline__ float sqrt_(float x) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU.SQRT
   return r;
 }
 __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
@@ -88,9 +88,13 @@ __device__ __forceinline__ bool isnan_(float x) { return isnan(x); }
 __device__ __forceinline__ bool isnan_(double x) { return isnan(x); }
 
 // quotient (see sqrt_)
-__device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float div_(float a, float b) {  // MUFU.RCP + FMUL
+  float r;
+  asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
 __device__ __forceinline__ double div_(double a, double b) { return a / b; }
-__device__ __forceinline__ float qdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float qdiv(float a, float b) { return div_(a, b); }
 __device__ __forceinline__ double qdiv(double a, double b) { return a / b; }
 
 // np.linalg.norm of a 2-vector; one definition for every distance so that adjacency,

@@ -432,6 +432,19 @@ __device__ __noinline__ void place_world(const KParams& p, const Smem<Real>& sm,
   }
 }
 
+// Four consecutive entries of a masked distance row (july:1625-1648): columns cb .. cb+3 of row r.
+template <typename Real>
+__device__ __forceinline__ void masked_dist4(const typename RT<Real>::V2* pw, const uint8_t* mk, typename RT<Real>::V2 a, bool mr,
+                                             int r, int cb, Real (&d)[4]) {
+  using V4 = typename RT<Real>::V4;
+  const V4 p01 = *reinterpret_cast<const V4*>(pw + cb), p23 = *reinterpret_cast<const V4*>(pw + cb + 2);
+  const uint32_t m4 = *reinterpret_cast<const uint32_t*>(mk + cb);
+  d[0] = (r == cb || mr || (m4 & 0xffu)) ? Real(0) : norm2(a.x - p01.x, a.y - p01.y);
+  d[1] = (r == cb + 1 || mr || (m4 & 0xff00u)) ? Real(0) : norm2(a.x - p01.z, a.y - p01.w);
+  d[2] = (r == cb + 2 || mr || (m4 & 0xff0000u)) ? Real(0) : norm2(a.x - p23.x, a.y - p23.y);
+  d[3] = (r == cb + 3 || mr || (m4 & 0xff000000u)) ? Real(0) : norm2(a.x - p23.z, a.y - p23.w);
+}
+
 // ---- the kernel ----------------------------------------------------------------------
 // Launch bounds picked by tools/sweep.py on a B200 (profiles/r1_sweep.txt): 128 threads with
 // >= 6 resident CTAs per SM (<= 85 registers) beat 256 x 1..4 on every workload measured.
@@ -1076,6 +1089,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
       const unsigned grp_mask = LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u);
       const unsigned lt_mask = (1u << sl) - 1u;
       const int nrows = nw * E;
+      const bool vec4 = (E & 3) == 0;
       for (int row0 = warp * rpw; row0 < nrows; row0 += nwarps * rpw) {
         const int row = row0 + sub;
         uint32_t w = 0, r = 0;
@@ -1087,16 +1101,37 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
         const bool mr = mk[r] != 0;
         Real* g_row = (live && p.out.adj) ? (Real*)p.out.adj + ((size_t)(w0 + w) * E + r) * E : nullptr;
         int n_env = 0, n_gnn = 0;
-        for (int c0 = 0; c0 < E; c0 += LPR) {
-          const int cc = c0 + sl;
-          Real d = Real(0);
-          if (live && cc < E) {
-            const V2 bb = pw[cc];
-            d = ((int)r == cc || mr || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
-            if (g_row) g_row[cc] = d;
+        if (vec4) {
+          // E % 4 == 0: a lane owns 4 consecutive columns -- two 128-bit position loads, one
+          // 32-bit mask load and one 128-bit adjacency store per 4 entries
+          for (int c0 = 0; c0 < E; c0 += 128) {
+            const int cb = c0 + 4 * lane;
+            if (live && cb < E) {
+              Real d[4];
+              masked_dist4<Real>(pw, mk, a, mr, (int)r, cb, d);
+              if (g_row) *reinterpret_cast<V4*>(g_row + cb) = RT<Real>::mk4(d[0], d[1], d[2], d[3]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                n_env += (d[q] > Real(0) && d[q] <= thr_env);
+                const float df = (float)d[q];
+                n_gnn += (df > 0.0f && df < thr_gnn);
+              }
+            }
           }
-          if (env_e) n_env += __popc((__ballot_sync(0xffffffffu, d > Real(0) && d <= thr_env) >> (sub * LPR)) & grp_mask);
-          if (gnn_e) { const float df = (float)d; n_gnn += __popc((__ballot_sync(0xffffffffu, df > 0.0f && df < thr_gnn) >> (sub * LPR)) & grp_mask); }
+          n_env = __reduce_add_sync(0xffffffffu, n_env);
+          n_gnn = __reduce_add_sync(0xffffffffu, n_gnn);
+        } else {
+          for (int c0 = 0; c0 < E; c0 += LPR) {
+            const int cc = c0 + sl;
+            Real d = Real(0);
+            if (live && cc < E) {
+              const V2 bb = pw[cc];
+              d = ((int)r == cc || mr || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
+              if (g_row) g_row[cc] = d;
+            }
+            if (env_e) n_env += __popc((__ballot_sync(0xffffffffu, d > Real(0) && d <= thr_env) >> (sub * LPR)) & grp_mask);
+            if (gnn_e) { const float df = (float)d; n_gnn += __popc((__ballot_sync(0xffffffffu, df > 0.0f && df < thr_gnn) >> (sub * LPR)) & grp_mask); }
+          }
         }
         if (live && sl == 0) { sm.rowoff_env[row] = n_env; sm.rowoff_gnn[row] = n_gnn; }
       }
@@ -1149,6 +1184,44 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           int32_t* gi = gnn_e ? p.out.gnn_edge_index + gb * 2 * cap : nullptr;
           Real* gea = gnn_e ? (Real*)p.out.gnn_edge_attr + gb * cap : nullptr;
           int b_env = live ? sm.rowoff_env[row] : 0, b_gnn = live ? sm.rowoff_gnn[row] : 0;
+          if (vec4) {
+            for (int c0 = 0; c0 < E; c0 += 128) {
+              const int cb = c0 + 4 * lane;
+              Real d[4] = {Real(0), Real(0), Real(0), Real(0)};
+              if (live && cb < E) masked_dist4<Real>(pw, mk, a, mr, (int)r, cb, d);
+#pragma unroll 1
+              for (int pass = 0; pass < 2; ++pass) {
+                if (!(pass == 0 ? env_e : gnn_e)) continue;
+                unsigned bits = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float df = (float)d[q];
+                  const bool on = pass == 0 ? (d[q] > Real(0) && d[q] <= thr_env) : (df > 0.0f && df < thr_gnn);
+                  bits |= (unsigned)on << q;
+                }
+                const int cnt = __popc(bits);
+                int inc = cnt;  // inclusive scan of the per-lane counts: columns are ordered by lane, then q
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                  const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                  if (lane >= o) inc += t;
+                }
+                int& base = pass == 0 ? b_env : b_gnn;
+                int slot = base + inc - cnt;
+                base += __shfl_sync(0xffffffffu, inc, 31);
+                int32_t* xi = pass == 0 ? ei : gi;
+                Real* xa = pass == 0 ? ea : gea;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if ((bits >> q) & 1u) {
+                    xi[slot] = (int32_t)r; xi[cap + slot] = cb + q;
+                    xa[slot] = pass == 0 ? d[q] : Real((float)d[q]);
+                    ++slot;
+                  }
+              }
+            }
+            continue;
+          }
           for (int c0 = 0; c0 < E; c0 += LPR) {
             const int cc = c0 + sl;
             Real d = Real(0);
