@@ -432,6 +432,32 @@ __device__ __noinline__ void place_world(const KParams& p, const Smem<Real>& sm,
   }
 }
 
+// -1 / 0 padding of one world's fixed-capacity edge buffers behind its last edge, by one warp:
+// 128-bit stores over the aligned middle, scalars at the ragged ends.
+template <typename T>
+__device__ __forceinline__ void fill_span(T* p, T v, int lo, int hi, int lane) {
+  constexpr int VW = 16 / (int)sizeof(T);
+  int a = lo;
+  while (a < hi && (reinterpret_cast<size_t>(p + a) & 15)) ++a;  // first 16-byte aligned element
+  if (lo + lane < a) p[lo + lane] = v;                            // head: fewer than VW elements
+  const int nv = (hi - a) / VW;
+  if (nv > 0) {
+    T vv[VW];
+#pragma unroll
+    for (int q = 0; q < VW; ++q) vv[q] = v;
+    const int4 v4 = *reinterpret_cast<const int4*>(vv);
+    int4* d4 = reinterpret_cast<int4*>(p + a);
+    for (int q = lane; q < nv; q += 32) d4[q] = v4;
+  }
+  for (int q = a + (nv > 0 ? nv : 0) * VW + lane; q < hi; q += 32) p[q] = v;
+}
+template <typename Real>
+__device__ __forceinline__ void pad_edges(int32_t* ei, Real* ea, int n, int cap, int lane) {
+  fill_span<int32_t>(ei, -1, n, cap, lane);
+  fill_span<int32_t>(ei + cap, -1, n, cap, lane);
+  fill_span<Real>(ea, Real(0), n, cap, lane);
+}
+
 // Four consecutive entries of a masked distance row (july:1625-1648): columns cb .. cb+3 of row r.
 template <typename Real>
 __device__ __forceinline__ void masked_dist4(const typename RT<Real>::V2* pw, const uint8_t* mk, typename RT<Real>::V2 a, bool mr,
@@ -1158,13 +1184,13 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           if (env_e) {
             int32_t* ei = p.out.edge_index + gb * 2 * cap;
             Real* ea = (Real*)p.out.edge_attr + gb * cap;
-            for (int q = run_env + lane; q < cap; q += 32) { ei[q] = -1; ei[cap + q] = -1; ea[q] = Real(0); }
+            pad_edges<Real>(ei, ea, run_env, cap, lane);
             if (lane == 0) p.out.num_edges[gb] = run_env;
           }
           if (gnn_e) {
             int32_t* gi = p.out.gnn_edge_index + gb * 2 * cap;
             Real* gea = (Real*)p.out.gnn_edge_attr + gb * cap;
-            for (int q = run_gnn + lane; q < cap; q += 32) { gi[q] = -1; gi[cap + q] = -1; gea[q] = Real(0); }
+            pad_edges<Real>(gi, gea, run_gnn, cap, lane);
             if (lane == 0) p.out.gnn_num_edges[gb] = run_gnn;
           }
         }
