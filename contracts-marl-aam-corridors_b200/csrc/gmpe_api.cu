@@ -258,6 +258,17 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
     h->stage_graph = pick_stage_graph(h->cfg, h->wpb);
     h->smem_bytes = f64 ? smem_for<double>(h->cfg, h->wpb, h->stage_graph) : smem_for<float>(h->cfg, h->wpb, h->stage_graph);
     h->fn = f64 ? (const void*)gmpe_step_kernel<double> : (const void*)gmpe_step_kernel<float>;
+    // fp32 instantiations with compile-time entity counts for the BASELINE shapes
+    const GmpeConfig& q = h->cfg;
+    const bool generic = getenv("GMPE_GENERIC_SHAPE") && atoi(getenv("GMPE_GENERIC_SHAPE"));
+    if (!f64 && !generic) {
+      if (q.num_agents == 16 && q.num_landmarks == 16 && q.num_obstacles == 8 && q.num_walls == 4 &&
+          q.scenario == GMPE_SCEN_NAV_GRAPH && q.dynamics == GMPE_DYN_DOUBLE_INTEGRATOR)
+        h->fn = (const void*)gmpe_step_kernel<float, 16, 16, 8, 4, GMPE_SCEN_NAV_GRAPH>;
+      else if (q.num_agents == 64 && q.num_landmarks == 64 && q.num_obstacles == 0 && q.num_walls == 0 &&
+               q.scenario == GMPE_SCEN_JULY_TUBE)
+        h->fn = (const void*)gmpe_step_kernel<float, 64, 64, 0, 0, GMPE_SCEN_JULY_TUBE>;
+    }
   }
   units = h->num_tiles;
   const void* fn = h->fn;

@@ -39,6 +39,19 @@ struct FastDiv {
   }
 };
 
+// Division by a divisor that is either a compile-time constant C (> 0: the compiler emits the
+// multiply-shift itself and folds it into the surrounding address arithmetic) or, for C == 0,
+// a launch-time constant handled by FastDiv.
+template <int C>
+struct CDiv {
+  FastDiv f;
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return C > 0 ? n / (uint32_t)(C > 0 ? C : 1) : f.div(n); }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    if (C > 0) { q = n / (uint32_t)(C > 0 ? C : 1); r = n - q * (uint32_t)C; }
+    else f.divmod(n, q, r);
+  }
+};
+
 // ---- Philox4x32-10, counter = (idx, episode, world_lo, world_hi), key = seed -------
 // Same specification as the CPU oracle (oracle/gmpe_oracle.c) so free-running batches
 // can be compared; the code is independent.

@@ -480,16 +480,28 @@ __device__ __forceinline__ void masked_dist4(const typename RT<Real>::V2* pw, co
 #ifndef GMPE_LB_MINBLOCKS
 #define GMPE_LB_MINBLOCKS 6
 #endif
-template <typename Real>
+// NC / LC / OC / WC > 0: entity counts known at compile time (instantiated for the BASELINE
+// shapes 16/16/8/4 and 64/64/0/0 in fp32); NC == 0: every count is a launch-time value.
+// SC: scenario known at compile time (GMPE_SCEN_*; the navigation instance also fixes the
+// force-physics double-integrator state), -1 = launch-time value.
+template <typename Real, int NC = 0, int LC = 0, int OC = 0, int WC = 0, int SC = -1>
 __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_kernel(const __grid_constant__ KParams p) {
   using V2 = typename RT<Real>::V2;
   using V4 = typename RT<Real>::V4;
   extern __shared__ __align__(32) unsigned char smem_raw[];
   const GmpeConfig& c = p.c;
-  const int N = c.num_agents, L = c.num_landmarks, O = c.num_obstacles, W = c.num_walls, E = p.E, F = p.F;
+  const int N = NC ? NC : c.num_agents, L = NC ? LC : c.num_landmarks, O = NC ? OC : c.num_obstacles, W = NC ? WC : c.num_walls;
+  const int E = NC ? NC + LC + OC + WC : p.E, F = p.F;
+  constexpr int EC = NC ? NC + LC + OC + WC : 0;
+  const CDiv<NC> dN{p.dN};
+  const CDiv<EC> dE{p.dE};
+  const CDiv<EC * EC> dEE{p.dEE};
+  const CDiv<LC> dL{p.dL};
+  const CDiv<OC> dO{p.dO};
+  const CDiv<WC> dW{p.dW};
   const int B = c.num_worlds, WPB = p.wpb;
-  const bool july = c.scenario == GMPE_SCEN_JULY_TUBE;
-  const bool heading = c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR;
+  const bool july = SC < 0 ? c.scenario == GMPE_SCEN_JULY_TUBE : SC == GMPE_SCEN_JULY_TUBE;
+  const bool heading = SC == GMPE_SCEN_NAV_GRAPH ? false : c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR;
   const bool do_info = (c.flags & GMPE_FLAG_INFO) != 0;
   const int tid = threadIdx.x, nthr = blockDim.x;
   Smem<Real> sm;
@@ -511,15 +523,15 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
     // ---------------- cooperative, coalesced loads of world-level state -------------
     for (int q = tid; q < nw * GMPE_WORLD_F; q += nthr) sm.wf[q] = g_wf[(size_t)w0 * GMPE_WORLD_F + q];
     for (int q = tid; q < nw * L; q += nthr) {
-      uint32_t lw, l; p.dL.divmod(q, lw, l);
+      uint32_t lw, l; dL.divmod(q, lw, l);
       sm.pos[lw * E + N + l] = ((const V2*)g_lm)[(size_t)w0 * L + q];
     }
     for (int q = tid; q < nw * O; q += nthr) {
-      uint32_t lw, o; p.dO.divmod(q, lw, o);
+      uint32_t lw, o; dO.divmod(q, lw, o);
       sm.pos[lw * E + N + L + o] = ((const V2*)g_ob)[(size_t)w0 * O + q];
     }
     for (int q = tid; q < nw * W; q += nthr) {
-      uint32_t lw, k; p.dW.divmod(q, lw, k);
+      uint32_t lw, k; dW.divmod(q, lw, k);
       const Real* src = g_wl + ((size_t)w0 * W + q) * GMPE_WALL_F;
       Real* dst = sm.wl + q * GMPE_WALL_F;
       Real o0 = src[0], a = src[1], e0 = src[2], e1 = src[3];
@@ -539,7 +551,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
     // ---------------- phase A: thread = (world, agent) -------------------------------
     const bool active = tid < nw * N;
     uint32_t lw = 0, i = 0;
-    if (active) p.dN.divmod(tid, lw, i);
+    if (active) dN.divmod(tid, lw, i);
     const int64_t b = w0 + (int64_t)lw;
     const size_t ga = (size_t)w0 * N + tid;  // global agent slot
     V4 s = RT<Real>::mk4(0, 0, 0, 0);
@@ -901,7 +913,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
     // disconnected mask per entity (july:1627-1648): done agents, and landmark l once agent l
     // reached it (goal_tracker[l] == l; goal_match_index = arange)
     for (int q = tid; q < nw * E; q += nthr) {
-      uint32_t w, k; p.dE.divmod(q, w, k);
+      uint32_t w, k; dE.divmod(q, w, k);
       const uint8_t* stw = sm.stpost + w * N;
       sm.mask[q] = k < (uint32_t)N ? stw[k] : ((k < (uint32_t)(2 * N) && k < (uint32_t)(N + L)) ? stw[k - N] : (uint8_t)0);
     }
@@ -914,7 +926,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
       } else {
         for (int q = tid; q < total; q += nthr) {
           uint32_t row = p.dF.div(q);
-          uint32_t w = p.dN.div(row);
+          uint32_t w = dN.div(row);
           if (sm.wwrite[w]) g_obs[q] = sm.obs[q];
         }
       }
@@ -933,7 +945,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
       Real* g_node = (Real*)p.out.node_obs + (size_t)w0 * N * E * 8;
       for (int row = warp * rpw + sub; row < nw * N; row += nwarps * rpw) {
         uint32_t w, j;
-        p.dN.divmod(row, w, j);
+        dN.divmod(row, w, j);
         if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
         const V2* pw = sm.pos + w * E;
         const V2 pe = pw[j], ve = sm.velpost[w * N + j];
@@ -959,8 +971,8 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
       const int total = nw * N * E;
       for (int q = tid; q < total; q += nthr) {
         uint32_t k, t2, j, w;
-        p.dE.divmod(q, t2, k);
-        p.dN.divmod(t2, w, j);
+        dE.divmod(q, t2, k);
+        dN.divmod(t2, w, j);
         if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
         const V2* pw = sm.pos + w * E;
         const V2 pe = pw[j], pk = pw[k], ve = sm.velpost[w * N + j];
@@ -991,8 +1003,8 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
       // pre-padded buffers that leave the SM as contiguous 128-bit stores.
       for (int q = tid; q < nw * EE; q += nthr) {
         uint32_t w, rc, r, cc;
-        p.dEE.divmod(q, w, rc);
-        p.dE.divmod(rc, r, cc);
+        dEE.divmod(q, w, rc);
+        dE.divmod(rc, r, cc);
         const V2* pw = sm.pos + w * E;
         const uint8_t* mk = sm.mask + w * E;
         V2 a = pw[r], bb = pw[cc];
@@ -1045,8 +1057,8 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
         const int total = nw * EE;
         for (int q = tid; q < total; q += nthr) {
           uint32_t w, rc, r, cc;
-          p.dEE.divmod(q, w, rc);
-          p.dE.divmod(rc, r, cc);
+          dEE.divmod(q, w, rc);
+          dE.divmod(rc, r, cc);
           if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
           const V2* pw = sm.pos + w * E;
           const uint8_t* mk = sm.mask + w * E;
@@ -1072,7 +1084,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
             uint32_t r = 0, cc = 0;
             Real d = Real(0);
             if (q < EE) {
-              p.dE.divmod(q, r, cc);
+              dE.divmod(q, r, cc);
               V2 a = pw[r], bb = pw[cc];
               d = (r == cc || mk[r] || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
             }
@@ -1120,7 +1132,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
         const int row = row0 + sub;
         uint32_t w = 0, r = 0;
         bool live = row < nrows;
-        if (live) { p.dE.divmod(row, w, r); live = p.mode == MODE_STEP || sm.wwrite[w]; }
+        if (live) { dE.divmod(row, w, r); live = p.mode == MODE_STEP || sm.wwrite[w]; }
         const V2* pw = sm.pos + w * E;
         const uint8_t* mk = sm.mask + w * E;
         const V2 a = pw[r];
@@ -1199,7 +1211,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           const int row = row0 + sub;
           uint32_t w = 0, r = 0;
           bool live = row < nrows;
-          if (live) { p.dE.divmod(row, w, r); live = p.mode == MODE_STEP || sm.wwrite[w]; }
+          if (live) { dE.divmod(row, w, r); live = p.mode == MODE_STEP || sm.wwrite[w]; }
           const V2* pw = sm.pos + w * E;
           const uint8_t* mk = sm.mask + w * E;
           const V2 a = pw[r];
