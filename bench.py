@@ -46,6 +46,12 @@ WORKLOADS = {
                   num_agents=3, num_landmarks=3, world_size=3, episode_length=200, goal_rew=30, collision_rew=5,
                   formation_rew=1, collaborative=False, use_dones=False, max_speed=2),
         worlds_per_gpu=131072),
+    # the rotation-invariant family (eval_scripts/commands_test_run.txt:37)
+    "three_phase_air_taxi_n3_b131072": dict(
+        args=dict(scenario_name="three_phase_graph", dynamics_type="air_taxi", num_agents=3, num_landmarks=3,
+                  world_size=3, episode_length=75, goal_rew=30, collision_rew=5, formation_rew=1,
+                  collaborative=False, use_dones=False, max_speed=2),
+        worlds_per_gpu=131072),
     # BASELINE.json configs[3]
     "navigation_graph_n16_o8_w4": dict(
         args=dict(scenario_name="navigation_graph", dynamics_type="double_integrator", num_agents=16,

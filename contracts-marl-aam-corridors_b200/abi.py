@@ -10,12 +10,12 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # error codes
 OK, E_INVALID, E_CUDA, E_NULL = 0, -1, -2, -3
 
-SCEN_JULY_TUBE, SCEN_NAV_GRAPH = 0, 1
+SCEN_JULY_TUBE, SCEN_NAV_GRAPH, SCEN_THREE_PHASE = 0, 1, 2
 DYN_DOUBLE_INTEGRATOR, DYN_UNICYCLE, DYN_AIR_TAXI = 0, 1, 2
 PHYS_KINEMATIC, PHYS_FORCE = 0, 1
 F32, F64 = 0, 1
@@ -84,14 +84,14 @@ class GmpeLayout(C.Structure):
         ("node_dim", C.c_int32), ("edge_cap", C.c_int32), ("info_dim", C.c_int32),
     ] + [(n, C.c_int64) for n in (
         "agent_state", "agent_aux", "agent_flags", "agent_cnt", "world_f", "world_i",
-        "landmarks", "obstacles", "walls", "obs", "node_obs", "adj", "reward", "done", "info",
+        "landmarks", "obstacles", "walls", "agent_ext", "obs", "node_obs", "adj", "reward", "done", "info",
         "edge_index", "edge_attr", "num_edges")]
 
 
 class GmpeState(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "agent_state", "agent_aux", "agent_flags", "agent_cnt", "world_f", "world_i",
-        "landmarks", "obstacles", "walls")]
+        "landmarks", "obstacles", "walls", "agent_ext")]
 
 
 class GmpeStepOut(C.Structure):
@@ -176,8 +176,8 @@ def layout_for(cfg: GmpeConfig) -> GmpeLayout:
     E = N + L + O + W
     lay.real_bytes = 8 if cfg.precision == F64 else 4
     lay.num_entities = E
-    lay.obs_dim = 19 if cfg.scenario == SCEN_JULY_TUBE else 6
-    lay.node_dim = 8
+    lay.obs_dim = {SCEN_JULY_TUBE: 19, SCEN_NAV_GRAPH: 6, SCEN_THREE_PHASE: 15}[cfg.scenario]
+    lay.node_dim = 7 if cfg.scenario == SCEN_THREE_PHASE else 8
     lay.edge_cap = E * (E - 1)
     lay.info_dim = INFO_K
     lay.agent_state = B * N * 4
@@ -189,6 +189,7 @@ def layout_for(cfg: GmpeConfig) -> GmpeLayout:
     lay.landmarks = B * L * 2
     lay.obstacles = B * O * 2
     lay.walls = B * W * WALL_F
+    lay.agent_ext = B * N * 2
     lay.obs = B * N * lay.obs_dim
     lay.node_obs = B * N * E * lay.node_dim
     lay.adj = B * E * E

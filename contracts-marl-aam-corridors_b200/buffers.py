@@ -12,7 +12,7 @@ import numpy as np
 from . import abi
 
 STATE_FIELDS = ("agent_state", "agent_aux", "agent_flags", "agent_cnt", "world_f", "world_i",
-                "landmarks", "obstacles", "walls")
+                "landmarks", "obstacles", "walls", "agent_ext")
 OUT_FIELDS = ("obs", "node_obs", "adj", "reward", "done", "info", "edge_index", "edge_attr",
               "num_edges", "gnn_edge_index", "gnn_edge_attr", "gnn_num_edges", "indiv_reward")
 #: optional float32 outputs (runner masks); only requested by DeviceGraphRollout
@@ -34,6 +34,7 @@ def shapes(cfg: abi.GmpeConfig) -> dict:
         "landmarks": ((B, L, 2), "real"),
         "obstacles": ((B, O, 2), "real"),
         "walls": ((B, W, abi.WALL_F), "real"),
+        "agent_ext": ((B, N, 2), "i32"),
         "obs": ((B, N, lay.obs_dim), "real"),
         "node_obs": ((B, N, E, lay.node_dim), "real"),
         "adj": ((B, E, E), "real"),

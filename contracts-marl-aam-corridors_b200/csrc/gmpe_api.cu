@@ -38,8 +38,11 @@ static int fail(gmpe_ctx* h, int code, const std::string& msg) {
   return code;
 }
 
+static int obs_dim_of(const GmpeConfig& c) { return c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : (c.scenario == GMPE_SCEN_THREE_PHASE ? 15 : 6); }
+static int node_dim_of(const GmpeConfig& c) { return c.scenario == GMPE_SCEN_THREE_PHASE ? 7 : 8; }
+
 static const char* validate(const GmpeConfig& c) {
-  if (c.scenario != GMPE_SCEN_JULY_TUBE && c.scenario != GMPE_SCEN_NAV_GRAPH) return "unknown scenario";
+  if (c.scenario != GMPE_SCEN_JULY_TUBE && c.scenario != GMPE_SCEN_NAV_GRAPH && c.scenario != GMPE_SCEN_THREE_PHASE) return "unknown scenario";
   if (c.dynamics < 0 || c.dynamics > 2) return "unknown dynamics";
   if (c.physics != GMPE_PHYS_KINEMATIC && c.physics != GMPE_PHYS_FORCE) return "unknown physics";
   if (c.precision != GMPE_F32 && c.precision != GMPE_F64) return "unknown precision";
@@ -48,6 +51,9 @@ static const char* validate(const GmpeConfig& c) {
   if (c.num_landmarks < c.num_agents) return "num_landmarks must be >= num_agents";
   if (c.num_obstacles < 0 || c.num_walls < 0) return "negative entity count";
   if (c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls > GMPE_MAX_ENTITIES) return "too many entities";
+  if (c.scenario == GMPE_SCEN_THREE_PHASE &&
+      !(c.num_agents == 3 && c.num_landmarks == 3 && c.num_obstacles == 0 && c.num_walls == 0 && c.physics == GMPE_PHYS_KINEMATIC))
+    return "three_phase_graph is served for num_agents == num_landmarks == 3 without obstacles / walls, kinematic step";
   if (c.scenario == GMPE_SCEN_JULY_TUBE && (c.num_obstacles || c.num_walls))
     return "july tube scenario supports num_obstacles == num_walls == 0 only (the reference graph builder raises, SURVEY G7)";
   if (c.physics == GMPE_PHYS_FORCE && c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR) return "force physics needs double_integrator state";
@@ -66,7 +72,7 @@ static int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } retu
 // otherwise.
 static void plan_tiles(const GmpeConfig& c, int threads, int* wpb, int* tiles) {
   const int E = c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls;
-  const int F = c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
+  const int F = obs_dim_of(c);
   const int vw = c.precision == GMPE_F64 ? 2 : 4;  // elements per 16 bytes
   int m = 1;
   const int counts[3] = {c.num_agents * F, E * E, E * (E - 1)};
@@ -84,7 +90,7 @@ static void plan_tiles(const GmpeConfig& c, int threads, int* wpb, int* tiles) {
 template <typename Real>
 static size_t smem_for(const GmpeConfig& c, int wpb, int stage_graph) {
   int E = c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls;
-  int F = c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
+  int F = obs_dim_of(c);
   return smem_layout<Real>(wpb, c.num_agents, E, c.num_walls, F, stage_graph, nullptr, nullptr);
 }
 
@@ -105,6 +111,7 @@ enum { KERNEL_TILE = 0, KERNEL_WORLD = 1, KERNEL_COOP = 2 };
 static int pick_kernel(const GmpeConfig& c) {
   const bool small = c.num_agents == 3 && c.num_landmarks == 3 && c.num_obstacles == 0 && c.num_walls == 0;
   if (!small) return KERNEL_TILE;
+  if (c.scenario == GMPE_SCEN_THREE_PHASE) return KERNEL_COOP;  // only the lane-per-agent kernel serves it
   if (const char* t = getenv("GMPE_FORCE_TILE")) if (atoi(t)) return KERNEL_TILE;
   if (const char* k = getenv("GMPE_KERNEL")) {
     if (!strcmp(k, "tile")) return KERNEL_TILE;
@@ -143,13 +150,14 @@ static void rebase_state(GmpeState& s, const GmpeConfig& c, int64_t b0, int64_t 
   shift_bytes(s.landmarks, b0 * c.num_landmarks * 2 * R);
   shift_bytes(s.obstacles, b0 * c.num_obstacles * 2 * R);
   shift_bytes(s.walls, b0 * c.num_walls * GMPE_WALL_F * R);
+  shift(s.agent_ext, b0 * N * 2);
 }
 
 static void rebase_out(GmpeStepOut& o, const GmpeConfig& c, int64_t b0, int64_t R) {
   const int64_t N = c.num_agents, E = N + c.num_landmarks + c.num_obstacles + c.num_walls, cap = E * (E - 1);
-  const int64_t F = c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
+  const int64_t F = obs_dim_of(c);
   shift_bytes(o.obs, b0 * N * F * R);
-  shift_bytes(o.node_obs, b0 * N * E * 8 * R);
+  shift_bytes(o.node_obs, b0 * N * E * node_dim_of(c) * R);
   shift_bytes(o.adj, b0 * E * E * R);
   shift_bytes(o.reward, b0 * N * R);
   shift(o.done, b0 * N);
@@ -176,8 +184,8 @@ int gmpe_layout(const GmpeConfig* cfg, GmpeLayout* out) {
   const int64_t E = N + L + O + W;
   out->real_bytes = cfg->precision == GMPE_F64 ? 8 : 4;
   out->num_entities = (int32_t)E;
-  out->obs_dim = cfg->scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
-  out->node_dim = 8;
+  out->obs_dim = obs_dim_of(*cfg);
+  out->node_dim = node_dim_of(*cfg);
   out->edge_cap = (int32_t)(E * (E - 1));
   out->info_dim = GMPE_INFO_K;
   out->agent_state = B * N * 4;
@@ -189,8 +197,9 @@ int gmpe_layout(const GmpeConfig* cfg, GmpeLayout* out) {
   out->landmarks = B * L * 2;
   out->obstacles = B * O * 2;
   out->walls = B * W * GMPE_WALL_F;
+  out->agent_ext = B * N * 2;
   out->obs = B * N * out->obs_dim;
-  out->node_obs = B * N * E * 8;
+  out->node_obs = B * N * E * out->node_dim;
   out->adj = B * E * E;
   out->reward = B * N;
   out->done = B * N;
@@ -228,13 +237,22 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
     h->wpb = GMPE_COOP_WARPS * (32 / 3);
     h->num_tiles = (cfg->num_worlds + h->wpb - 1) / h->wpb;
     h->stage_graph = 0;
-    if (f64) {
-      h->fn = july ? (const void*)gmpe_step_coop_kernel<double, GMPE_SCEN_JULY_TUBE, 3> : (const void*)gmpe_step_coop_kernel<double, GMPE_SCEN_NAV_GRAPH, 3>;
-      h->smem_bytes = GMPE_COOP_WARPS * (july ? CoopTraits<double, GMPE_SCEN_JULY_TUBE, 3>::SLAB_BYTES : CoopTraits<double, GMPE_SCEN_NAV_GRAPH, 3>::SLAB_BYTES);
-    } else {
-      h->fn = july ? (const void*)gmpe_step_coop_kernel<float, GMPE_SCEN_JULY_TUBE, 3> : (const void*)gmpe_step_coop_kernel<float, GMPE_SCEN_NAV_GRAPH, 3>;
-      h->smem_bytes = GMPE_COOP_WARPS * (july ? CoopTraits<float, GMPE_SCEN_JULY_TUBE, 3>::SLAB_BYTES : CoopTraits<float, GMPE_SCEN_NAV_GRAPH, 3>::SLAB_BYTES);
-    }
+    const int sc = cfg->scenario;
+#define GMPE_COOP_PICK(REAL)                                                                              \
+    do {                                                                                                  \
+      if (sc == GMPE_SCEN_JULY_TUBE) {                                                                    \
+        h->fn = (const void*)gmpe_step_coop_kernel<REAL, GMPE_SCEN_JULY_TUBE, 3>;                         \
+        h->smem_bytes = GMPE_COOP_WARPS * CoopTraits<REAL, GMPE_SCEN_JULY_TUBE, 3>::SLAB_BYTES;           \
+      } else if (sc == GMPE_SCEN_THREE_PHASE) {                                                           \
+        h->fn = (const void*)gmpe_step_coop_kernel<REAL, GMPE_SCEN_THREE_PHASE, 3>;                       \
+        h->smem_bytes = GMPE_COOP_WARPS * CoopTraits<REAL, GMPE_SCEN_THREE_PHASE, 3>::SLAB_BYTES;         \
+      } else {                                                                                            \
+        h->fn = (const void*)gmpe_step_coop_kernel<REAL, GMPE_SCEN_NAV_GRAPH, 3>;                         \
+        h->smem_bytes = GMPE_COOP_WARPS * CoopTraits<REAL, GMPE_SCEN_NAV_GRAPH, 3>::SLAB_BYTES;           \
+      }                                                                                                   \
+    } while (0)
+    if (f64) GMPE_COOP_PICK(double); else GMPE_COOP_PICK(float);
+#undef GMPE_COOP_PICK
   } else if (h->small == KERNEL_WORLD) {
     // one thread per world, warps are independent: see gmpe_small.cuh
     h->threads = 32 * GMPE_SMALL_WARPS;
@@ -359,12 +377,13 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   if (!st->agent_state || !st->agent_aux || !st->agent_flags || !st->agent_cnt || !st->world_f || !st->world_i || !st->landmarks)
     return fail(h, GMPE_E_NULL, "a required state array is NULL");
   if ((c.num_obstacles && !st->obstacles) || (c.num_walls && !st->walls)) return fail(h, GMPE_E_NULL, "obstacles / walls array is NULL");
+  if (c.scenario == GMPE_SCEN_THREE_PHASE && !st->agent_ext) return fail(h, GMPE_E_NULL, "three_phase_graph needs state.agent_ext");
   if (mode == MODE_STEP && (!act || !out->reward || !out->done)) return fail(h, GMPE_E_NULL, "gmpe_step needs action_idx, out.reward and out.done");
   if ((c.flags & GMPE_FLAG_ENV_EDGES) && out->edge_index && (!out->edge_attr || !out->num_edges)) return fail(h, GMPE_E_NULL, "edge_attr / num_edges missing");
   if ((c.flags & GMPE_FLAG_GNN_EDGES) && out->gnn_edge_index && (!out->gnn_edge_attr || !out->gnn_num_edges)) return fail(h, GMPE_E_NULL, "gnn_edge_attr / gnn_num_edges missing");
   // feature rows leave the SM as 256-bit stores (store_row8): torch / cudaMalloc buffers are
   // 256-byte aligned, an arbitrary caller pointer must at least be 32-byte aligned
-  if ((reinterpret_cast<size_t>(out->node_obs) & 31) || (reinterpret_cast<size_t>(out->info) & 31))
+  if ((node_dim_of(c) == 8 && (reinterpret_cast<size_t>(out->node_obs) & 31)) || (reinterpret_cast<size_t>(out->info) & 31))
     return fail(h, GMPE_E_INVALID, "out.node_obs and out.info must be 32-byte aligned");
   KParams p;
   memset(&p, 0, sizeof(p));
@@ -396,7 +415,7 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   p.stage_graph = h->stage_graph;
   const int N = c.num_agents, L = c.num_landmarks, O = c.num_obstacles, W = c.num_walls;
   p.E = N + L + O + W;
-  p.F = c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
+  p.F = obs_dim_of(c);
   p.dN = FastDiv::make(N); p.dE = FastDiv::make(p.E); p.dL = FastDiv::make(L); p.dO = FastDiv::make(O);
   p.dW = FastDiv::make(W); p.dF = FastDiv::make(p.F); p.d16 = FastDiv::make(16);
 #ifdef GMPE_EXPERIMENTS

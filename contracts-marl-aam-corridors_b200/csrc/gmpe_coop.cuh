@@ -43,7 +43,8 @@ namespace gmpe {
 template <typename Real, int SCEN, int N>
 struct CoopTraits {
   static constexpr int E = 2 * N, EE = E * E, CAP = E * (E - 1);
-  static constexpr int F = SCEN == GMPE_SCEN_JULY_TUBE ? 19 : 6;
+  static constexpr int F = SCEN == GMPE_SCEN_JULY_TUBE ? 19 : (SCEN == GMPE_SCEN_THREE_PHASE ? 15 : 6);
+  static constexpr int ND = SCEN == GMPE_SCEN_THREE_PHASE ? 7 : 8;  // node feature width
   static constexpr int R = (int)sizeof(Real);
   static constexpr int WPW = 32 / N;   // worlds per warp
   static constexpr int AL = WPW * N;   // active lanes
@@ -53,7 +54,9 @@ struct CoopTraits {
   static constexpr int ADJ_BYTES = up16(WPW * EE * R) + 16;
   static constexpr int EIDX_BYTES = up16(WPW * 2 * CAP * 4) + 16;
   static constexpr int EATTR_BYTES = up16(WPW * CAP * R) + 16;
-  static constexpr int ROUND_A = OBS_BYTES + ADJ_BYTES;
+  // 7-wide node rows (three_phase) are not whole sectors: the warp's rows are staged as one span
+  static constexpr int NODE_BYTES = ND == 8 ? 0 : up16(AL * E * ND * R) + 16;
+  static constexpr int ROUND_A = OBS_BYTES + ADJ_BYTES + NODE_BYTES;
   static constexpr int ROUND_B = EIDX_BYTES + EATTR_BYTES;
   static constexpr int SLAB_BYTES = up16(ROUND_A > ROUND_B ? ROUND_A : ROUND_B);
 };
@@ -95,6 +98,9 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
   using T = CoopTraits<Real, SCEN, N>;
   constexpr int E = T::E, EE = T::EE, CAP = T::CAP, F = T::F, WPW = T::WPW, AL = T::AL;
   constexpr bool july = SCEN == GMPE_SCEN_JULY_TUBE;
+  constexpr bool tp = SCEN == GMPE_SCEN_THREE_PHASE;  // three_phase_graph.py ("tp" in the citations)
+  constexpr bool tube = july || tp;                   // scenarios with a tube frame in world_f
+  constexpr int ND = T::ND;
   extern __shared__ __align__(32) unsigned char smem_raw[];
   const GmpeConfig& c = p.c;
   const int B = c.num_worlds;
@@ -144,7 +150,9 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     int st_pre = flw & 0xff, pp = (flw >> 8) & 0xff, pr = (flw >> 16) & 0xff, gr = (flw >> 24) & 0xff;
     Real wf[12];
     Real dsum0 = Real(0);
-    if (july) {
+    int cool = 0;  // tp: entry_reward_cooldown (tp:348)
+    if (tp) cool = p.st.agent_ext[ga * 2];
+    if (tube) {
       const Real* gw_ = g_wf + (size_t)b * GMPE_WORLD_F;
 #pragma unroll
       for (int q = 0; q < 12; ++q) wf[q] = gw_[q];
@@ -168,8 +176,10 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     }
 
     V2 vpre = RT<Real>::mk2(0, 0), vpost = vpre;
-    Real hx = Real(1), hy = Real(0);
+    Real hx = Real(1), hy = Real(0);    // heading unit vector before reward() ...
+    Real hpx = Real(1), hpy = Real(0);  // ... and after it (reset_velocity re-draws the heading)
     int st_post = st_pre, ph_obs = 0;
+    uint32_t nbr_excl = 0;              // tp: agents that are done at observation(i) time (tp:1185-1186)
     bool rs = false;  // this world is (re)placed in this launch
     bool wr = valid;  // this world's tensors are emitted by this launch
     Real rew = Real(0);
@@ -222,6 +232,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       if (sp > Real(0)) { hx = div_(s.z, sp); hy = div_(s.w, sp); }
     }
     vpost = vpre;
+    hpx = hx; hpy = hy;
+    Real spd_obs = heading ? s.w : norm2(s.z, s.w);  // state.speed at observation time (tp:1244)
 
     // positions / goals of the whole world, by shuffle
     Real PX[N], PY[N], LX[N], LY[N];
@@ -248,6 +260,13 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       if (july) {
         ph = tube_phase<Real>(wf, s.x, s.y, pp_eff);  // observation-time call may promote pp (july:727)
         reach = (ph == 2) && (pr != 0) && (d_goal < thr_goal) && !st_pre;
+      } else if (tp) {
+        Real ts, ty;
+        tp_tube_coords<Real>(wf, s.x, s.y, ts, ty);
+        ph = tp_phase<Real>(ts, ty, wf[GMPE_WF_L], wf[GMPE_WF_HALF_W], pp, pr);
+        cool -= cool > 0;  // get_agent_phase counts the cooldown down on every call (tp:652-654):
+        cool -= cool > 0;  // once from observation(), once from reward()
+        reach = (ph == 2) && (d_goal < thr_goal) && !st_pre;  // tp:1110-1119
       } else {
         reach = (d_goal < thr_goal) && (c.flags & GMPE_FLAG_USE_DONES) && !st_pre;
       }
@@ -255,7 +274,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       if (reach) {  // agent.status = True; state.reset_velocity() (july:1188-1190, core.py:324-333)
         st_post = 1;
         if (heading) {
-          if (july) {
+          if (tube) {
             Real th = p.theta ? ((const Real*)p.theta)[ga] : Real(NAN);
             if (isnan_(th))
               th = Real(philox_uniform(c.seed, c.world_offset + b, (uint32_t)wep,
@@ -266,7 +285,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
           Real sn, cs;
           sincos_(s.z, &sn, &cs);
           vpost = RT<Real>::mk2(s.w * cs, s.w * sn);
-        } else { s.z = Real(0); s.w = Real(0); vpost = RT<Real>::mk2(0, 0); }
+          hpx = cs; hpy = sn;
+        } else { s.z = Real(0); s.w = Real(0); vpost = RT<Real>::mk2(0, 0); hpx = Real(1); hpy = Real(0); }
       }
 
       // ---------------- pass B: terms that look at other agents -----------------
@@ -282,7 +302,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         const bool close = d < sep;
         ncoll_rew += (close && !st_k && !st_pre);    // is_collision at reward(i) time (july:907-914)
         ncoll_info += (close && !st_k && !st_post);  // ... at info_callback(i) time (july:785)
-        if (july) {  // front / back neighbours along the own heading (july:1136-1143)
+        if (tp && st_k) nbr_excl |= 1u << k;
+        if (tube) {  // front / back neighbours along the own heading (july:1136-1143, tp:991-1003)
           const Real rx = PX[k] - s.x, ry = PY[k] - s.y;
           const Real proj = rx * hx + ry * hy;
           if (proj > Real(0)) { if (front < 0 || proj < fproj) { front = k; fproj = proj; fdist = d; } }
@@ -324,6 +345,44 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         pp = cur;
         rew = clip(rew, -Real(4) * coll, goal * Real(5));
         rew = clip(rew, Real(c.min_reward), Real(c.max_reward));
+      } else if (tp) {  // Scenario.reward (tp:957-1159)
+        rew -= Real(ncoll_rew) * coll;
+        Real ts, ty;
+        tp_tube_coords<Real>(wf, s.x, s.y, ts, ty);
+        const Real L = wf[GMPE_WF_L], hw = wf[GMPE_WF_HALF_W];
+        const bool valid_exit = tp_in_exit_gate(ts, ty, L, hw);
+        if (ph == 2 && ph > pp + 1) rew -= goal;  // tp:1018-1019
+        if (ph == pp + 1 && pr == ph - 1) {       // tp:1028-1042
+          if (ph == 1 && tp_in_entrance_gate(ts, ty, L, hw) && cool == 0) { rew += goal; cool = c.episode_length; pr = 1; }
+          else if (ph == 2) { rew += goal; pr = 2; }
+        }
+        // |heading error| to the corridor axis: sin / cos of (theta - corridor_heading) from the unit vectors
+        const Real ex_ = wf[GMPE_WF_E_X], ey_ = wf[GMPE_WF_E_Y];
+        const Real he = abs_(atan2_(ex_ * hy - ey_ * hx, ex_ * hx + ey_ * hy));
+        if (ph == 0) {  // tp:1044-1063
+          const Real d = tp_entrance_gate_distance(ts, ty, hw);
+          rew -= d;
+          if (d < Real(c.world_size * 0.1)) rew -= he * Real(c.formation_rew) * Real(0.5);
+        } else if (ph == 1) {  // tp:1065-1108
+          if (front >= 0) { const Real diff = fdist - sep; sp_err += diff < Real(0) ? abs_(diff) : Real(0); }
+          if (back >= 0) { const Real diff = bdist - sep; sp_err += diff < Real(0) ? abs_(diff) : Real(0); }
+          if (sp_err > Real(0)) cnt[GMPE_AC_SPACING_VIOL] += 1;
+          rew -= sp_err * Real(c.formation_rew);
+          rew -= tp_exit_gate_distance(ts, ty, L, hw);
+          cnt[GMPE_AC_STEPS_IN_CORRIDOR] += 1;
+          rew -= he * Real(c.formation_rew) * Real(0.1);
+        } else {  // tp:1110-1123
+          if (d_goal < thr_goal) { if (reach) rew += goal * Real(5); }
+          else rew -= d_goal;
+        }
+        if (pr == 1 && ph == 0) cnt[GMPE_AC_CONFORMANCE] += 1;
+        if (ph > pr) pr = ph;
+        if (ph < pp) rew -= coll;
+        if (ph < pr) rew -= coll;
+        pp = ph;
+        if (tp_in_tube_rect(ts, ty, L, hw) && ph != 1 && !valid_exit) rew -= coll;  // tp:1145-1147
+        if (ts > L && pr < 1) rew -= goal;                                           // tp:1149-1151
+        rew = clip(rew, -Real(4) * coll, goal * Real(5));
       } else {
         rew -= Real(ncoll_rew) * coll;
         if (d_goal < thr_goal) rew += goal; else rew -= d_goal;
@@ -408,7 +467,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         ((V2*)g_aux)[ga] = aux;
         g_fl[ga] = (uint32_t)st_post | ((uint32_t)pp << 8) | ((uint32_t)pr << 16) | ((uint32_t)gr << 24);
         if (i == 0) g_wi[(size_t)b * GMPE_WORLD_I + GMPE_WI_STEP] = wstep;
-        if (july && do_info && i == N - 1) g_wf[(size_t)b * GMPE_WORLD_F + GMPE_WF_DELTA_SPACING] = dsum;
+        if (tube && do_info && i == N - 1) g_wf[(size_t)b * GMPE_WORLD_F + GMPE_WF_DELTA_SPACING] = dsum;
+        if (tp) p.st.agent_ext[ga * 2] = cool;
         if (do_info) {
           int4* gc = (int4*)(g_cnt + ga * GMPE_AGENT_CNT);
           gc[0] = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
@@ -438,7 +498,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         aux.y = ((const V2*)p.rst.agent_aux)[ga].y;
       } else {
         const Placed<Real, N> pl = place_small<Real, SCEN, N>(c, c.world_offset + b, (uint32_t)wep);
-        if (july) {
+        if (tube) {
 #pragma unroll
           for (int q = 0; q < 12; ++q) wf[q] = pl.wf[q];
         }
@@ -450,7 +510,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       // persist the world-level arrays
       if (i == 0) {
         Real* gw_ = g_wf + (size_t)b * GMPE_WORLD_F;
-        if (july || p.has_rst) {
+        if (tube || p.has_rst) {
 #pragma unroll
           for (int q = 0; q < 12; ++q) gw_[q] = wf[q];
         }
@@ -461,11 +521,26 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       ((V2*)g_lm)[ga] = lmi;
       aux.x = Real(0);
       st_post = 0;
-      if (heading) { Real sn, cs; sincos_(s.z, &sn, &cs); vpre = RT<Real>::mk2(s.w * cs, s.w * sn); }
-      else vpre = RT<Real>::mk2(s.z, s.w);
+      hx = Real(1); hy = Real(0);
+      if (heading) { sincos_(s.z, &hy, &hx); vpre = RT<Real>::mk2(s.w * hx, s.w * hy); }
+      else {
+        vpre = RT<Real>::mk2(s.z, s.w);
+        const Real sp = norm2(s.z, s.w);
+        if (sp > Real(0)) { hx = div_(s.z, sp); hy = div_(s.w, sp); }
+      }
       vpost = vpre;
+      hpx = hx; hpy = hy;
+      spd_obs = heading ? s.w : norm2(s.z, s.w);
+      nbr_excl = 0;
       // observations of the fresh episode replace the terminal ones (env_wrappers.py:867-873)
       ph_obs = july ? tube_phase<Real>(wf, s.x, s.y, pp) : 0;
+      if (tp) {  // phase_reached and the cooldown were cleared by reset_world (tp:346-348)
+        Real ts, ty;
+        tp_tube_coords<Real>(wf, s.x, s.y, ts, ty);
+        ph_obs = tp_phase<Real>(ts, ty, wf[GMPE_WF_L], wf[GMPE_WF_HALF_W], pp, 0);
+        p.st.agent_ext[ga * 2] = 0;
+        p.st.agent_ext[ga * 2 + 1] = 0;
+      }
       ((V4*)g_as)[ga] = s;
       ((V2*)g_aux)[ga] = aux;
       g_fl[ga] = (uint32_t)0 | ((uint32_t)pp << 8);
@@ -512,7 +587,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     // ---------------- emission: node features of ego = this lane's agent ---------------------
     // _get_entity_feat_relative (july:1694-1771): [rel_vel, rel_pos, rel_goal, occupied, type];
     // ego i sees agents <= i with their post-reward velocity, agents > i pre-reward
-    if (p.out.node_obs && wr) {
+    if (ND == 8 && p.out.node_obs && wr) {
       Real* g_node = (Real*)p.out.node_obs + ga * (size_t)(E * 8);
 #pragma unroll
       for (int k = 0; k < N; ++k) {
@@ -539,6 +614,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     Real* g_adj = p.out.adj ? (Real*)p.out.adj + (size_t)wbase * EE : nullptr;
     unsigned char* obs_region = slab;
     unsigned char* adj_region = slab + T::OBS_BYTES;
+    unsigned char* node_region = slab + T::OBS_BYTES + T::ADJ_BYTES;  // 7-wide node rows only
+    Real* g_nodew = (ND != 8 && p.out.node_obs) ? (Real*)p.out.node_obs + (size_t)wbase * N * E * ND : nullptr;
     Real* adj_s = reinterpret_cast<Real*>(adj_region + (reinterpret_cast<size_t>(g_adj) & 15)) + wl * EE;
     Real* obs_s = reinterpret_cast<Real*>(obs_region + (reinterpret_cast<size_t>(g_obs) & 15)) + lane * F;
     // rows i and N + i of the masked distance matrix (july:1625-1648): done agents and the
@@ -547,12 +624,14 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const bool dead = st_post || STF[k];
+      // tp never records goal_tracker (tp:1119 is commented out): landmarks stay connected there
+      const bool lm_i_dead = tp ? false : (bool)st_post, lm_k_dead = tp ? false : (bool)STF[k];
       // agent i -> agent k, agent i -> landmark k
       row_a[k] = (k == i || dead) ? Real(0) : daa[k];
-      row_a[N + k] = dead ? Real(0) : dal[k];
+      row_a[N + k] = (st_post || lm_k_dead) ? Real(0) : dal[k];
       // landmark i -> agent k, landmark i -> landmark k
-      row_l[k] = dead ? Real(0) : norm2(lmi.x - PX[k], lmi.y - PY[k]);
-      row_l[N + k] = (k == i || dead) ? Real(0) : norm2(lmi.x - LX[k], lmi.y - LY[k]);
+      row_l[k] = (lm_i_dead || STF[k]) ? Real(0) : norm2(lmi.x - PX[k], lmi.y - PY[k]);
+      row_l[N + k] = (k == i || lm_i_dead || lm_k_dead) ? Real(0) : norm2(lmi.x - LX[k], lmi.y - LY[k]);
     }
     if (lane_used) {
       if (july) {  // Scenario.observation (july:1337-1463)
@@ -576,6 +655,40 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         o[15] = wf[GMPE_WF_EXIT_X] - s.x; o[16] = wf[GMPE_WF_EXIT_Y] - s.y;
         o[17] = wf[GMPE_WF_WIDTH];
         o[18] = Real(ph_obs);
+      } else if (tp) {  // Scenario.observation (tp:1161-1250): everything in the agent's heading frame
+        Real d1 = Real(0), d2 = Real(0);
+        V2 r1 = RT<Real>::mk2(0, 0), r2 = RT<Real>::mk2(0, 0);
+        int seen = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {  // the two nearest agents that are not done (tp:1182-1196)
+          if (k == i || ((nbr_excl >> k) & 1u)) continue;
+          const Real rx = PX[k] - s.x, ry = PY[k] - s.y, d = daa[k];
+          if (seen == 0 || d < d1) { d2 = d1; r2 = r1; d1 = d; r1 = RT<Real>::mk2(rx, ry); }
+          else if (seen == 1 || d < d2) { d2 = d; r2 = RT<Real>::mk2(rx, ry); }
+          ++seen;
+        }
+        Real* o = obs_s;
+        o[0] = trunc32(hx); o[1] = trunc32(hy);
+        o[2] = trunc32(spd_obs);
+        Real ax, ay;
+        rot_into(hx, hy, lmi.x - s.x, lmi.y - s.y, ax, ay);
+        o[3] = trunc32(ax); o[4] = trunc32(ay);
+        rot_into(hx, hy, trunc32(r1.x), trunc32(r1.y), ax, ay);  // float32 cast BEFORE the rotation (tp:1199)
+        o[5] = trunc32(ax); o[6] = trunc32(ay);
+        rot_into(hx, hy, trunc32(r2.x), trunc32(r2.y), ax, ay);
+        o[7] = trunc32(ax); o[8] = trunc32(ay);
+        Real ts, ty;
+        tp_tube_coords<Real>(wf, s.x, s.y, ts, ty);
+        const Real L = wf[GMPE_WF_L], hw = wf[GMPE_WF_HALF_W];
+        o[9] = trunc32(clip(div_(ts, L), Real(-2), Real(2)));
+        o[10] = trunc32(clip(div_(ty, hw + Real(1e-9)), Real(-2), Real(2)));
+        o[11] = trunc32(div_(tp_exit_gate_distance(ts, ty, L, hw), L + Real(1e-9)));
+        const Real ex_ = wf[GMPE_WF_E_X], ey_ = wf[GMPE_WF_E_Y];
+        Real cn = ex_ * hx + ey_ * hy, sn_ = ex_ * hy - ey_ * hx;  // cos / sin of (theta - corridor_heading)
+        const Real nrm = norm2(cn, sn_);                             // e is a unit vector up to 1e-9
+        cn = div_(cn, nrm); sn_ = div_(sn_, nrm);
+        o[12] = trunc32(cn); o[13] = trunc32(sn_);
+        o[14] = Real(ph_obs);
       } else if (obs_direct) {
         if (wr && g_obs) {
           V2* o = reinterpret_cast<V2*>((Real*)p.out.obs + ga * F);
@@ -590,16 +703,41 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         for (int q = 0; q < E; ++q) { adj_s[i * E + q] = row_a[q]; adj_s[(N + i) * E + q] = row_l[q]; }
       }
     }
+    if (ND != 8 && lane_used && g_nodew) {
+      // _get_entity_feat_relative (tp:1391-1430): float32 differences rotated into the ego's
+      // (post-reward) heading frame; [rel_vel, rel_pos, rel_goal, type], 7 Reals per node
+      Real* nd = reinterpret_cast<Real*>(node_region + (reinterpret_cast<size_t>(g_nodew) & 15)) + lane * (E * ND);
+      const Real pex = trunc32(s.x), pey = trunc32(s.y), vex = trunc32(vpost.x), vey = trunc32(vpost.y);
+#pragma unroll
+      for (int k = 0; k < E; ++k) {
+        Real pkx, pky, vkx = Real(0), vky = Real(0);
+        if (k < N) {
+          const bool post = k <= i;
+          pkx = trunc32(PX[k]); pky = trunc32(PY[k]);
+          vkx = trunc32(post ? VQX[k] : VPX[k]); vky = trunc32(post ? VQY[k] : VPY[k]);
+        } else { pkx = trunc32(LX[k - N]); pky = trunc32(LY[k - N]); }
+        Real f[7];
+        rot_into(hpx, hpy, trunc32(vkx - vex), trunc32(vky - vey), f[0], f[1]);
+        rot_into(hpx, hpy, trunc32(pkx - pex), trunc32(pky - pey), f[2], f[3]);
+        if (k < N) rot_into(hpx, hpy, trunc32(trunc32(LX[k]) - pex), trunc32(trunc32(LY[k]) - pey), f[4], f[5]);
+        else { f[4] = f[2]; f[5] = f[3]; }
+        f[6] = k < N ? Real(0) : Real(1);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) nd[k * ND + q] = trunc32(f[q]);
+        nd[k * ND + 6] = f[6];
+      }
+    }
     if (adj_direct && wr && p.out.adj) {  // two rows of E Reals each, 8/16-byte aligned (E is even)
       V2* ra = reinterpret_cast<V2*>((Real*)p.out.adj + (size_t)b * EE + (size_t)i * E);
       V2* rl = reinterpret_cast<V2*>((Real*)p.out.adj + (size_t)b * EE + (size_t)(N + i) * E);
 #pragma unroll
       for (int q = 0; q < N; ++q) { ra[q] = RT<Real>::mk2(row_a[2 * q], row_a[2 * q + 1]); rl[q] = RT<Real>::mk2(row_l[2 * q], row_l[2 * q + 1]); }
     }
-    if (!obs_direct || !adj_direct) {
+    if (!obs_direct || !adj_direct || ND != 8) {
       __syncwarp();
       if (!obs_direct && g_obs) copy_span<Real, N * F>(g_obs, obs_region, nwv * N * F, all_worlds, wmask, lane);
       if (!adj_direct && g_adj) copy_span<Real, EE>(g_adj, adj_region, nwv * EE, all_worlds, wmask, lane);
+      if (ND != 8 && g_nodew) copy_span<Real, N * E * ND>(g_nodew, node_region, nwv * N * E * ND, all_worlds, wmask, lane);
       __syncwarp();
     }
 

@@ -110,6 +110,19 @@ __device__ __forceinline__ double div_(double a, double b) { return a / b; }
 __device__ __forceinline__ float qdiv(float a, float b) { return div_(a, b); }
 __device__ __forceinline__ double qdiv(double a, double b) { return a / b; }
 
+__device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+// (x + pi) % (2 pi) - pi of the reference's heading errors (three_phase_graph.py:1058, 1106, 1222)
+__device__ __forceinline__ float wrap_pi(float x) { return x - 6.283185307179586f * rintf(x * 0.15915494309189535f); }
+__device__ __forceinline__ double wrap_pi(double x) {
+  double m = fmod(x + 3.14159265358979323846, 6.283185307179586476925286766559);
+  if (m < 0) m += 6.283185307179586476925286766559;
+  return m - 3.14159265358979323846;
+}
+// np.hypot
+__device__ __forceinline__ float hypot_(float x, float y) { return sqrt_(x * x + y * y); }
+__device__ __forceinline__ double hypot_(double x, double y) { return hypot(x, y); }
+
 // np.linalg.norm of a 2-vector; one definition for every distance so that adjacency,
 // edges and collision tests see identical values.
 template <typename Real>

@@ -146,11 +146,16 @@ __device__ __noinline__ Placed<Real, N> place_small(const GmpeConfig& c, int64_t
   const Real sep = Real(c.separation_dist);
 #pragma unroll
   for (int q = 0; q < 12; ++q) o.wf[q] = Real(0);
-  if (SCEN == GMPE_SCEN_JULY_TUBE) {
+  if (SCEN == GMPE_SCEN_JULY_TUBE || SCEN == GMPE_SCEN_THREE_PHASE) {
+    // three_phase_graph.py:416-587 differs from july:440-613 by one extra draw (tube length) and
+    // two spawn constants
+    constexpr bool tp = SCEN == GMPE_SCEN_THREE_PHASE;
+    const double jit = tp ? 0.3 : 0.2, spread = tp ? 3.0 : 5.0;
     (void)philox_uniform01(seed, gw, ep, idx++);  // wall_length draw (july:368), value unused
     const double width = fmax(3 * c.entity_size * 2.5, ws * 0.15);
     const double angle = philox_uniform(seed, gw, ep, idx++, -1.5707963267948966, 1.5707963267948966);
-    const double tl = ws * 0.8;
+    double tl = ws * 0.8;
+    if (tp) tl += philox_uniform(seed, gw, ep, idx++, -ws * 0.3, ws * 0.1);  // tp:503
     double ca, sa;
     sincos(angle, &sa, &ca);
     const double ent0 = sa * (tl / 4), ent1 = ca * (tl / 4), ext0 = sa * (-tl / 4), ext1 = ca * (-tl / 4);
@@ -167,10 +172,10 @@ __device__ __noinline__ Placed<Real, N> place_small(const GmpeConfig& c, int64_t
       Real px, py;
       bool bad;
       do {
-        const double jx = 0.2 * philox_uniform(seed, gw, ep, idx, -ws, ws);
-        const double jy = 0.2 * philox_uniform(seed, gw, ep, idx + 1, -ws, ws);
+        const double jx = jit * philox_uniform(seed, gw, ep, idx, -ws, ws);
+        const double jy = jit * philox_uniform(seed, gw, ep, idx + 1, -ws, ws);
         idx += 2;
-        const double d = (ws + k) / 5;
+        const double d = (ws + k) / spread;
         px = Real(ent0 + d * sa + jx); py = Real(ent1 + d * ca + jy);
         bad = false;
 #pragma unroll

@@ -269,6 +269,58 @@ __device__ __forceinline__ int tube_phase(const Real* wf, Real px, Real py, int&
   return 0;
 }
 
+// ---- three_phase_graph.py ("tp"): the rotation-invariant scenario family -------------------
+// _tube_coords (tp:592-598): float32 position, float32 normal
+template <typename Real>
+__device__ __forceinline__ void tp_tube_coords(const Real* wf, Real px, Real py, Real& s, Real& y) {
+  const Real rx = trunc32(px) - wf[GMPE_WF_ENT_X], ry = trunc32(py) - wf[GMPE_WF_ENT_Y];
+  s = rx * wf[GMPE_WF_E_X] + ry * wf[GMPE_WF_E_Y];
+  y = rx * wf[GMPE_WF_N_X] + ry * wf[GMPE_WF_N_Y];
+}
+template <typename Real>
+__device__ __forceinline__ bool tp_in_tube_rect(Real s, Real y, Real L, Real hw) {  // tp:600-601
+  return (Real(-0.05) <= s) && (s <= L + Real(0.05)) && (abs_(y) <= hw + Real(0.05));
+}
+template <typename Real>
+__device__ __forceinline__ bool tp_in_entrance_gate(Real s, Real y, Real L, Real hw) {  // tp:603-607, 584-585
+  return (-(Real(0.02) * L) - Real(0.05) <= s) && (s <= Real(0.08) * L + Real(0.05)) && (abs_(y) <= hw + Real(0.05));
+}
+template <typename Real>
+__device__ __forceinline__ bool tp_in_exit_gate(Real s, Real y, Real L, Real hw) {  // tp:618-621, 586-587
+  return (L - Real(0.02) * L - Real(0.05) <= s) && (s <= L + Real(0.08) * L + Real(0.05)) && (abs_(y) <= hw + Real(0.05));
+}
+template <typename Real>
+__device__ __forceinline__ Real tp_entrance_gate_distance(Real s, Real y, Real hw) {  // tp:610-615
+  return hypot_(abs_(s), y - clip(y, -hw, hw));
+}
+template <typename Real>
+__device__ __forceinline__ Real tp_exit_gate_distance(Real s, Real y, Real L, Real hw) {  // tp:624-633
+  const Real ds = L - s > Real(0) ? L - s : Real(0);
+  return hypot_(ds, y - clip(y, -hw, hw));
+}
+// get_agent_phase (tp:639-705); previous_phase / phase_reached are only read
+template <typename Real>
+__device__ __forceinline__ int tp_phase(Real s, Real y, Real L, Real hw, int pp, int pr) {
+  const bool in_tube = tp_in_tube_rect(s, y, L, hw), passed = s > L;
+  const bool valid_exit = tp_in_exit_gate(s, y, L, hw);
+  if (!in_tube && !passed) return 0;
+  if (in_tube) {
+    if (pp == 0) return tp_in_entrance_gate(s, y, L, hw) ? 1 : 0;
+    return valid_exit ? 2 : 1;  // pp is 1 or 2 here
+  }
+  if (pr >= 1) {  // passed the exit plane
+    if (pp == 1 && valid_exit) return 2;
+    if (pp == 2) return 2;
+  }
+  return 0;
+}
+// get_rotated_position_from_relative (tp:90-97) with the ego heading as a unit vector (hx, hy)
+template <typename Real>
+__device__ __forceinline__ void rot_into(Real hx, Real hy, Real vx, Real vy, Real& ox, Real& oy) {
+  ox = hx * vx + hy * vy;
+  oy = -hy * vx + hx * vy;
+}
+
 // is_obstacle_collision (july:864-890): obstacles within 2*(size_o + size), walls as a
 // 1.5*size band around the segment.
 template <typename Real>

@@ -205,7 +205,7 @@ class BatchedGraphMPE:
         b += R * N + N                 # reward + done out
         b += R * abi.WORLD_F + 2 * 4   # world frame in, step counter r+w
         b += 2 * R * (L + O) + abi.WALL_F * R * W
-        b += R * F * N + R * 8 * N * E + R * E * E
+        b += R * F * N + R * self.layout.node_dim * N * E + R * E * E
         if c.flags & abi.FLAG_INFO:
             b += 2 * (4 * abi.AGENT_CNT * N) + R * abi.INFO_K * N
         if c.flags & abi.FLAG_ENV_EDGES:

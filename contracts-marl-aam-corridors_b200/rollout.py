@@ -38,7 +38,7 @@ class DeviceGraphRollout:
         self.collaborative = bool(cfg.flags & abi.FLAG_COLLABORATIVE)
         # storage the step kernel writes into (slot t+1 of each)
         self._obs = torch.zeros((T1, B, N, F), dtype=real, device=dev)
-        self._node_obs = torch.zeros((T1, B, N, E, 8), dtype=real, device=dev)
+        self._node_obs = torch.zeros((T1, B, N, E, engine.layout.node_dim), dtype=real, device=dev)
         self._adj = torch.zeros((T1, B, E, E), dtype=real, device=dev)
         self._reward = torch.zeros((self.T, B, N), dtype=real, device=dev)
         self._done = torch.zeros((self.T, B, N), dtype=torch.uint8, device=dev)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GMPE_ABI_VERSION 6
+#define GMPE_ABI_VERSION 7
 
 /* error codes */
 #define GMPE_OK 0
@@ -39,6 +39,9 @@ extern "C" {
 /* GmpeConfig.scenario */
 #define GMPE_SCEN_JULY_TUBE 0 /* nav_metered_one_goal_graph_rotate_tube_july.py */
 #define GMPE_SCEN_NAV_GRAPH 1 /* navigation_graph-class, defined-by-build */
+#define GMPE_SCEN_THREE_PHASE 2 /* three_phase_graph.py: rotation-invariant fp32 features, 15-d obs,
+                                   7-d nodes, exit gate, random tube length;
+                                   served for N = L = 3, O = W = 0 */
 /* GmpeConfig.dynamics -- multiagent/core.py:23-26 EntityDynamicsType */
 #define GMPE_DYN_DOUBLE_INTEGRATOR 0
 #define GMPE_DYN_UNICYCLE 1
@@ -163,12 +166,12 @@ typedef struct GmpeConfig {
 typedef struct GmpeLayout {
   int32_t real_bytes;   /* 4 or 8 */
   int32_t num_entities; /* E = N+L+O+W */
-  int32_t obs_dim;      /* F_obs: 19 july, 6 nav */
-  int32_t node_dim;     /* F_node: 8 */
+  int32_t obs_dim;      /* F_obs: 19 july, 6 nav, 15 three_phase */
+  int32_t node_dim;     /* F_node: 8 (7 three_phase) */
   int32_t edge_cap;     /* E*(E-1) */
   int32_t info_dim;     /* GMPE_INFO_K */
   int64_t agent_state, agent_aux, agent_flags, agent_cnt;
-  int64_t world_f, world_i, landmarks, obstacles, walls;
+  int64_t world_f, world_i, landmarks, obstacles, walls, agent_ext;
   int64_t obs, node_obs, adj, reward, done, info;
   int64_t edge_index, edge_attr, num_edges;
 } GmpeLayout;
@@ -185,13 +188,16 @@ typedef struct GmpeState {
   void* landmarks;      /* Real [B][L][2]                                                              */
   void* obstacles;      /* Real [B][O][2]  (may be NULL when O == 0)                                   */
   void* walls;          /* Real [B][W][GMPE_WALL_F] (may be NULL when W == 0)                          */
+  int32_t* agent_ext;   /* i32  [B][N][2]: entry_reward_cooldown (three_phase_graph.py:348,652-654,1037),
+                           spare.  GMPE_SCEN_THREE_PHASE only; may be NULL for the other scenarios      */
 } GmpeState;
 
 /* Per-step outputs (device pointers, caller-owned).  Any pointer may be NULL to
  * skip that output, except reward/done for gmpe_step. */
 typedef struct GmpeStepOut {
   void* obs;           /* Real [B][N][F_obs]      Scenario.observation (july:1337-1463)                */
-  void* node_obs;      /* Real [B][N][E][F_node]  Scenario.graph_observation (july:1584-1649)          */
+  void* node_obs;      /* Real [B][N][E][F_node]  Scenario.graph_observation (july:1584-1649,
+                                                  three_phase_graph.py:1280-1445)                      */
   void* adj;           /* Real [B][E][E]          masked cached_dist_mag; the reference returns the SAME
                                                   ndarray for all N agents -> one copy     */
   void* reward;        /* Real [B][N]             Scenario.reward (july:1105-1221)                     */

@@ -206,6 +206,7 @@ typedef struct {
   double* lm;    /* [L][2] */
   double* ob;    /* [O][2] */
   double* wl;    /* [W][4] */
+  int32_t* ext;  /* [N][2] (three_phase: entry_reward_cooldown, spare) or NULL */
   /* scratch for the current step */
   double pos[MAXE][2];
   double dist[MAXE][MAXE];
@@ -225,6 +226,7 @@ static void bind_world(World* w, const GmpeConfig* c, const GmpeState* st, int64
   w->lm = (double*)st->landmarks + b * w->L * 2;
   w->ob = st->obstacles ? (double*)st->obstacles + b * w->O * 2 : NULL;
   w->wl = st->walls ? (double*)st->walls + b * w->W * GMPE_WALL_F : NULL;
+  w->ext = st->agent_ext ? st->agent_ext + b * w->N * 2 : NULL;
 }
 
 static int is_kin_heading(const GmpeConfig* c) { return c->dynamics != GMPE_DYN_DOUBLE_INTEGRATOR; }
@@ -672,6 +674,272 @@ static void july_info(World* w, int i, double* info) {
   info[GMPE_INFO_MIN_TIME] = w->aux[i * 2 + 1];
 }
 
+
+/* ------------------------------------------------------------------ three_phase scenario */
+/* "tp" = multiagent/custom_scenarios/three_phase_graph.py: the rotation-invariant family
+ * (SURVEY 8f rank 3).  reset_world / info_callback / is_collision / min_time are identical to
+ * july (diff of tp:315-399, 723-815, 847-956 against july:339-420, 741-829, 864-973 is empty up
+ * to a float32 cast and one extra info key), so those are shared. */
+static double agent_theta(const World* w, int i) { /* state.theta; arctan2(vy, vx) for the DI (core:188-189) */
+  const double* s = w->as + i * 4;
+  return is_kin_heading(w->c) ? s[2] : atan2(s[3], s[2]);
+}
+/* get_rotated_position_from_relative tp:90-97: float64 rotation matrix times the vector */
+static void rot_rel(double h, double vx, double vy, double out[2]) {
+  double c = cos(h), s = sin(h);
+  out[0] = c * vx + s * vy;
+  out[1] = -s * vx + c * vy;
+}
+static double pymod2pi(double x) { /* Python float %: result takes the sign of the (positive) divisor */
+  double m = fmod(x, TWO_PI);
+  if (m < 0) m += TWO_PI;
+  return m;
+}
+static double tp_entrance_gate_distance(double s, double y, double hw) { /* tp:610-615 */
+  double cy = clipd(y, -hw, hw);
+  return hypot(fabs(s), y - cy);
+}
+static double tp_exit_gate_distance(double s, double y, double L, double hw) { /* tp:624-633, penalize_backward=False */
+  double cy = clipd(y, -hw, hw);
+  double ds = L - s > 0.0 ? L - s : 0.0;
+  return hypot(ds, y - cy);
+}
+static int tp_in_tube_rect(double s, double y, double L, double hw) { return (-0.05 <= s && s <= L + 0.05) && (fabs(y) <= hw + 0.05); }
+static int tp_in_entrance_gate(double s, double y, double L, double hw) { /* tp:603-607, ratios tp:584-585 */
+  double gf = 0.08 * L, gb = 0.02 * L;
+  return (-gb - 0.05 <= s && s <= gf + 0.05) && (fabs(y) <= hw + 0.05);
+}
+static int tp_in_exit_gate(double s, double y, double L, double hw) { /* tp:618-621, ratios tp:586-587 */
+  double eb = 0.02 * L, ef = 0.08 * L;
+  return (L - eb - 0.05 <= s && s <= L + ef + 0.05) && (fabs(y) <= hw + 0.05);
+}
+
+/* get_agent_phase tp:639-705: decrements the entry cooldown on EVERY call (observation and
+ * reward both call it); does not touch previous_phase */
+static int tp_get_agent_phase(World* w, int i) {
+  const double* p = w->as + i * 4;
+  double s, y, L = w->wf[GMPE_WF_L], hw = w->wf[GMPE_WF_HALF_W];
+  tube_coords(w, p, &s, &y);
+  int in_tube = tp_in_tube_rect(s, y, L, hw);
+  int passed = s > L;
+  int valid_entrance = tp_in_entrance_gate(s, y, L, hw), valid_exit = tp_in_exit_gate(s, y, L, hw);
+  if (w->ext[i * 2] > 0) w->ext[i * 2] -= 1;
+  int pp = w->fl[i * 4 + GMPE_AF_PREV_PHASE];
+  if (!in_tube && !passed) return 0;
+  if (in_tube) {
+    if (pp == 0) return valid_entrance ? 1 : 0;
+    if (pp == 1 && valid_exit) return 2;
+    if (pp == 2 && valid_exit) return 2;
+    return 1;
+  }
+  if (passed && w->fl[i * 4 + GMPE_AF_PHASE_REACHED] >= 1) {
+    if (pp == 1 && valid_exit) return 2;
+    if (pp == 2) return 2;
+    return 0;
+  }
+  return 0;
+}
+
+/* Scenario.observation tp:1161-1250 -> 15 float32 values */
+static void tp_observation(World* w, int i, double* o) {
+  const double* p = w->as + i * 4;
+  double h = agent_theta(w, i);
+  double speed = is_kin_heading(w->c) ? p[3] : norm2(p[2], p[3]);
+  double g[2];
+  rot_rel(h, w->lm[i * 2] - p[0], w->lm[i * 2 + 1] - p[1], g); /* goal_match_index = arange (tp:325) */
+  double nd[MAXN], nr[MAXN][2];
+  int order[MAXN], m = 0;
+  for (int k = 0; k < w->N; ++k) { /* tp:1182-1191: done agents are not neighbours */
+    if (k == i || w->fl[k * 4 + GMPE_AF_STATUS]) continue;
+    nr[m][0] = w->as[k * 4] - p[0]; nr[m][1] = w->as[k * 4 + 1] - p[1];
+    nd[m] = norm2(nr[m][0], nr[m][1]);
+    order[m] = m; ++m;
+  }
+  for (int a = 1; a < m; ++a) { /* list.sort is stable */
+    int key = order[a], b = a - 1;
+    while (b >= 0 && nd[order[b]] > nd[key]) { order[b + 1] = order[b]; --b; }
+    order[b + 1] = key;
+  }
+  double nn[4] = {0, 0, 0, 0};
+  for (int q = 0; q < 2 && q < m; ++q) { /* np.asarray(vec, float32) BEFORE the rotation (tp:1199) */
+    double r[2];
+    rot_rel(h, (double)(float)nr[order[q]][0], (double)(float)nr[order[q]][1], r);
+    nn[2 * q] = r[0]; nn[2 * q + 1] = r[1];
+  }
+  int phase = tp_get_agent_phase(w, i);
+  double s, y, L = w->wf[GMPE_WF_L], hw = w->wf[GMPE_WF_HALF_W];
+  tube_coords(w, p, &s, &y);
+  double he = pymod2pi(h - atan2(w->wf[GMPE_WF_E_Y], w->wf[GMPE_WF_E_X]) + PI_D) - PI_D;
+  double raw[15] = {cos(h), sin(h), speed, g[0], g[1], nn[0], nn[1], nn[2], nn[3],
+                    clipd(s / L, -2.0, 2.0), clipd(y / (hw + 1e-9), -2.0, 2.0),
+                    tp_exit_gate_distance(s, y, L, hw) / (L + 1e-9), cos(he), sin(he), (double)phase};
+  for (int q = 0; q < 15; ++q) o[q] = (double)(float)raw[q]; /* .astype(np.float32), tp:1250 */
+}
+
+/* Scenario.reward tp:957-1159 */
+static double tp_reward(World* w, int i, double theta_draw) {
+  const GmpeConfig* c = w->c;
+  double rew = 0;
+  int phase = tp_get_agent_phase(w, i);
+  double* st = w->as + i * 4;
+  uint8_t* fl = w->fl + i * 4;
+  int32_t* cnt = w->cnt + i * GMPE_AGENT_CNT;
+  for (int a = 0; a < w->N; ++a) { /* tp:965-970 */
+    if (a == i) continue;
+    if (is_collision(w, a, i)) rew -= c->collision_rew;
+  }
+  double theta = agent_theta(w, i);
+  double hx = cos(theta), hy = sin(theta);
+  double s, y, L = w->wf[GMPE_WF_L], hw = w->wf[GMPE_WF_HALF_W];
+  tube_coords(w, st, &s, &y);
+  int valid_exit = tp_in_exit_gate(s, y, L, hw);
+  int front = -1, back = -1;
+  double fproj = 0, bproj = 0;
+  for (int k = 0; k < w->N; ++k) { /* tp:991-1003 */
+    if (k == i) continue;
+    double proj = (w->as[k * 4] - st[0]) * hx + (w->as[k * 4 + 1] - st[1]) * hy;
+    if (proj > 0) { if (front < 0 || proj < fproj) { front = k; fproj = proj; } }
+    else { if (back < 0 || proj > bproj) { back = k; bproj = proj; } }
+  }
+  int pp = fl[GMPE_AF_PREV_PHASE];
+  if (phase == 2 && phase > pp + 1) rew -= c->goal_rew; /* tp:1018-1019 */
+  if (phase == pp + 1 && fl[GMPE_AF_PHASE_REACHED] == phase - 1) { /* tp:1028-1042 */
+    if (phase == 1 && tp_in_entrance_gate(s, y, L, hw) && w->ext[i * 2] == 0) {
+      rew += c->goal_rew;
+      w->ext[i * 2] = c->episode_length; /* phase_reward_cooldown_steps = episode_length (tp:255) */
+      fl[GMPE_AF_PHASE_REACHED] = 1;
+    } else if (phase == 2) {
+      rew += c->goal_rew;
+      fl[GMPE_AF_PHASE_REACHED] = 2;
+    }
+  }
+  double corridor_heading = atan2(w->wf[GMPE_WF_E_Y], w->wf[GMPE_WF_E_X]);
+  if (phase == 0) { /* tp:1044-1063 */
+    double d = tp_entrance_gate_distance(s, y, hw);
+    rew -= d;
+    double he = fabs(pymod2pi(theta - corridor_heading + PI_D) - PI_D);
+    if (d < c->world_size * 0.1) rew -= he * c->formation_rew * 0.5;
+  } else if (phase == 1) { /* tp:1065-1108 */
+    double spacing_error = 0;
+    if (front >= 0) {
+      double diff = norm2(w->as[front * 4] - st[0], w->as[front * 4 + 1] - st[1]) - c->separation_dist;
+      spacing_error += diff < 0 ? fabs(diff) : 0;
+    }
+    if (back >= 0) {
+      double diff = norm2(w->as[back * 4] - st[0], w->as[back * 4 + 1] - st[1]) - c->separation_dist;
+      spacing_error += diff < 0 ? fabs(diff) : 0;
+    }
+    if (spacing_error > 0) cnt[GMPE_AC_SPACING_VIOL] += 1;
+    rew -= spacing_error * c->formation_rew;
+    rew -= tp_exit_gate_distance(s, y, L, hw);
+    cnt[GMPE_AC_STEPS_IN_CORRIDOR] += 1;
+    w->wf[GMPE_WF_DELTA_SPACING] += spacing_error;
+    double he = fabs(pymod2pi(theta - corridor_heading + PI_D) - PI_D);
+    rew -= he * c->formation_rew * 0.1;
+  } else if (phase == 2) { /* tp:1110-1123; goal_tracker is NOT updated here (line commented out) */
+    double d = norm2(st[0] - w->lm[i * 2], st[1] - w->lm[i * 2 + 1]);
+    if (d < c->goal_dist_thresh) {
+      if (!fl[GMPE_AF_STATUS]) {
+        fl[GMPE_AF_STATUS] = 1;
+        if (is_kin_heading(c)) { st[2] = theta_draw; st[3] = c->v_min; }
+        else { st[2] = 0; st[3] = 0; }
+        rew += c->goal_rew * 5;
+      }
+    } else rew -= d;
+  }
+  if (fl[GMPE_AF_PHASE_REACHED] == 1 && phase == 0) cnt[GMPE_AC_CONFORMANCE] += 1;
+  if (phase > fl[GMPE_AF_PHASE_REACHED]) fl[GMPE_AF_PHASE_REACHED] = (uint8_t)phase;
+  if (phase < fl[GMPE_AF_PREV_PHASE]) rew -= c->collision_rew;
+  if (phase < fl[GMPE_AF_PHASE_REACHED]) rew -= c->collision_rew;
+  fl[GMPE_AF_PREV_PHASE] = (uint8_t)phase;
+  if (tp_in_tube_rect(s, y, L, hw) && phase != 1 && !valid_exit) rew -= c->collision_rew; /* tp:1145-1147 */
+  if (s > L && fl[GMPE_AF_PHASE_REACHED] < 1) rew -= c->goal_rew;                             /* tp:1149-1151 */
+  return clipd(rew, -4 * c->collision_rew, c->goal_rew * 5);
+}
+
+/* _get_entity_feat_relative tp:1391-1430: 7 float32 features per node, float32 differences
+ * rotated into the ego heading frame with a float64 matrix */
+static void tp_node_features(World* w, int ego, double* out /* [E][7] */) {
+  double ve64[2];
+  p_vel(w, ego, ve64);
+  float pe[2] = {(float)w->as[ego * 4], (float)w->as[ego * 4 + 1]}, ve[2] = {(float)ve64[0], (float)ve64[1]};
+  double h = agent_theta(w, ego);
+  for (int k = 0; k < w->E; ++k) {
+    float pk[2], vk[2] = {0.0f, 0.0f};
+    if (k < w->N) {
+      double v64[2];
+      p_vel(w, k, v64);
+      pk[0] = (float)w->as[k * 4]; pk[1] = (float)w->as[k * 4 + 1];
+      vk[0] = (float)v64[0]; vk[1] = (float)v64[1];
+    } else { pk[0] = (float)w->pos[k][0]; pk[1] = (float)w->pos[k][1]; }
+    double rp[2], rv[2], rg[2];
+    rot_rel(h, (double)(float)(pk[0] - pe[0]), (double)(float)(pk[1] - pe[1]), rp);
+    rot_rel(h, (double)(float)(vk[0] - ve[0]), (double)(float)(vk[1] - ve[1]), rv);
+    if (k < w->N) {
+      float gx = (float)w->lm[k * 2], gy = (float)w->lm[k * 2 + 1]; /* landmark_poses[goal_match_index[entity.id]] */
+      rot_rel(h, (double)(float)(gx - pe[0]), (double)(float)(gy - pe[1]), rg);
+    } else { rg[0] = rp[0]; rg[1] = rp[1]; }
+    double* f = out + k * 7;
+    f[0] = (double)(float)rv[0]; f[1] = (double)(float)rv[1];
+    f[2] = (double)(float)rp[0]; f[3] = (double)(float)rp[1];
+    f[4] = (double)(float)rg[0]; f[5] = (double)(float)rg[1];
+    f[6] = k < w->N ? 0.0 : 1.0; /* entity_mapping: agent 0, landmark 1 */
+  }
+}
+
+/* graph_observation mask tp:1331-1343: goal_tracker is never set in this scenario, so only
+ * done agents are disconnected */
+static void tp_mask_adj(World* w) {
+  for (int a = 0; a < w->N; ++a)
+    if (w->fl[a * 4 + GMPE_AF_STATUS])
+      for (int b = 0; b < w->E; ++b) { w->dist[a][b] = 0.0; w->dist[b][a] = 0.0; }
+}
+
+/* random_scenario + setup_tube_params tp:416-587 */
+static void tp_random_scenario(World* w) {
+  const GmpeConfig* c = w->c;
+  uint64_t seed = c->seed;
+  int64_t gw = c->world_offset + w->b;
+  uint32_t ep = (uint32_t)w->wi[GMPE_WI_EPISODE], idx = 0;
+  double ws = c->world_size;
+  (void)uni(seed, gw, ep, idx++, 0.2, 0.8); /* wall_length draw, tp:343 (value unused) */
+  double width = fmax(3 * c->entity_size * 2.5, ws * 0.15);
+  double angle = uni(seed, gw, ep, idx++, -PI_D / 2, PI_D / 2);
+  double tl = ws * 0.8;
+  tl += uni(seed, gw, ep, idx++, -ws * 0.3, ws * 0.1); /* tp:503 */
+  double ca = cos(angle), sa = sin(angle);
+  double ent[2] = {sa * (tl / 4), ca * (tl / 4)};
+  double ext[2] = {sa * (-tl / 4), ca * (-tl / 4)};
+  double L = norm2(ext[0] - ent[0], ext[1] - ent[1]) + 1e-9;
+  double e[2] = {(ext[0] - ent[0]) / L, (ext[1] - ent[1]) / L};
+  w->wf[GMPE_WF_ENT_X] = ent[0]; w->wf[GMPE_WF_ENT_Y] = ent[1];
+  w->wf[GMPE_WF_EXIT_X] = ext[0]; w->wf[GMPE_WF_EXIT_Y] = ext[1];
+  w->wf[GMPE_WF_E_X] = e[0]; w->wf[GMPE_WF_E_Y] = e[1];
+  w->wf[GMPE_WF_N_X] = (double)(float)(-e[1]); w->wf[GMPE_WF_N_Y] = (double)(float)e[0];
+  w->wf[GMPE_WF_L] = L; w->wf[GMPE_WF_HALF_W] = width * 0.5;
+  w->wf[GMPE_WF_WIDTH] = width; w->wf[GMPE_WF_ANGLE] = angle;
+  int k = 0;
+  while (k < w->N) { /* tp:424-443 */
+    double jx = 0.3 * uni(seed, gw, ep, idx, -ws, ws), jy = 0.3 * uni(seed, gw, ep, idx + 1, -ws, ws);
+    idx += 2;
+    double d = (ws + k) / 3;
+    double p[2] = {ent[0] + d * sa + jx, ent[1] + d * ca + jy};
+    int bad = 0;
+    for (int a = 0; a < k && !bad; ++a)
+      if (norm2(w->as[a * 4] - p[0], w->as[a * 4 + 1] - p[1]) < c->separation_dist) bad = 1;
+    if (bad) continue;
+    double* s = w->as + k * 4;
+    s[0] = p[0]; s[1] = p[1];
+    if (is_kin_heading(c)) { s[2] = uni(seed, gw, ep, idx++, 0, TWO_PI); s[3] = c->v_min; }
+    else { s[2] = 0; s[3] = 0; }
+    ++k;
+  }
+  for (int l = 0; l < w->L; ++l) { /* set_landmarks_in_point, utils.py:177-187 */
+    w->lm[l * 2] = ext[0] + sa * (-ws / 3);
+    w->lm[l * 2 + 1] = ext[1] + ca * (-ws / 3);
+  }
+}
+
 /* ------------------------------------------------------------------ nav scenario (D1) */
 /* navigation_graph-class scenario: absent from the reference, defined by the
  * build as a composition of reference pieces.  6-d observation
@@ -736,6 +1004,7 @@ static void reset_counters(World* w) { /* reset_world july:339-374 */
     cnt[GMPE_AC_AGENT_COLL] = 0; cnt[GMPE_AC_OBST_COLL] = 0;
     cnt[GMPE_AC_TIME_REQ_I] = -1; cnt[GMPE_AC_DIST_TRAV_I] = -1; cnt[GMPE_AC_DIST_LEFT_I] = -1;
     w->aux[i * 2] = 0.0;
+    if (w->ext) { w->ext[i * 2] = 0; w->ext[i * 2 + 1] = 0; } /* entry_reward_cooldown, tp:348 */
   }
   w->wf[GMPE_WF_DELTA_SPACING] = 0.0;
   w->wi[GMPE_WI_STEP] = 0;
@@ -856,26 +1125,43 @@ static void write_graph_outputs(World* w, const GmpeStepOut* out) {
 }
 
 /* MultiAgentGraphEnv.reset env:1066-1081 -> reset_world july:339-420 */
+static int obs_dim_of(const GmpeConfig* c) { return c->scenario == GMPE_SCEN_JULY_TUBE ? 19 : (c->scenario == GMPE_SCEN_THREE_PHASE ? 15 : 6); }
+static int node_dim_of(const GmpeConfig* c) { return c->scenario == GMPE_SCEN_THREE_PHASE ? 7 : 8; }
+static void scen_observation(World* w, int i, double* o) {
+  switch (w->c->scenario) {
+    case GMPE_SCEN_JULY_TUBE: july_observation(w, i, o); break;
+    case GMPE_SCEN_THREE_PHASE: tp_observation(w, i, o); break;
+    default: nav_observation(w, i, o);
+  }
+}
+static void scen_node_features(World* w, int i, double* out) {
+  if (w->c->scenario == GMPE_SCEN_THREE_PHASE) tp_node_features(w, i, out); else node_features(w, i, out);
+}
+static void scen_mask_adj(World* w) {
+  if (w->c->scenario == GMPE_SCEN_THREE_PHASE) tp_mask_adj(w); else mask_adj(w);
+}
+
 static void reset_world(World* w, const GmpeStepInject* inj, const GmpeStepOut* out) {
   const GmpeConfig* c = w->c;
-  int odim = c->scenario == GMPE_SCEN_JULY_TUBE ? 19 : 6;
+  int odim = obs_dim_of(c), ndim = node_dim_of(c);
   reset_counters(w);
   if (inj && inj->reset_state) adopt_injected(w, inj->reset_state);
   else {
-    if (c->scenario == GMPE_SCEN_JULY_TUBE) july_random_scenario(w); else nav_random_scenario(w);
+    if (c->scenario == GMPE_SCEN_JULY_TUBE) july_random_scenario(w);
+    else if (c->scenario == GMPE_SCEN_THREE_PHASE) tp_random_scenario(w);
+    else nav_random_scenario(w);
     for (int i = 0; i < w->N; ++i) /* min_time july:941-951 */
       w->aux[i * 2 + 1] = norm2(w->as[i * 4] - w->lm[i * 2], w->as[i * 4 + 1] - w->lm[i * 2 + 1]) / c->max_speed;
   }
   w->wi[GMPE_WI_EPISODE] += 1;
   calculate_distances(w); /* initialize_min_time_distance_graph july:735-739 */
   for (int i = 0; i < w->N; ++i) {
-    if (out->obs) {
-      double* o = (double*)out->obs + (w->b * w->N + i) * odim;
-      if (c->scenario == GMPE_SCEN_JULY_TUBE) july_observation(w, i, o); else nav_observation(w, i, o);
-    } else if (c->scenario == GMPE_SCEN_JULY_TUBE) (void)get_agent_phase(w, i);
-    if (out->node_obs) node_features(w, i, (double*)out->node_obs + (w->b * w->N + i) * w->E * 8);
+    if (out->obs) scen_observation(w, i, (double*)out->obs + (w->b * w->N + i) * odim);
+    else if (c->scenario == GMPE_SCEN_JULY_TUBE) (void)get_agent_phase(w, i);
+    else if (c->scenario == GMPE_SCEN_THREE_PHASE) (void)tp_get_agent_phase(w, i);
+    if (out->node_obs) scen_node_features(w, i, (double*)out->node_obs + (w->b * w->N + i) * w->E * ndim);
   }
-  mask_adj(w);
+  scen_mask_adj(w);
   write_graph_outputs(w, out);
 }
 
@@ -884,8 +1170,7 @@ static void reset_world(World* w, const GmpeStepInject* inj, const GmpeStepOut* 
 static void step_world(World* w, const int32_t* act, const GmpeStepInject* inj, const GmpeStepOut* out, int use_rk45) {
   const GmpeConfig* c = w->c;
   int N = w->N, E = w->E;
-  int july = c->scenario == GMPE_SCEN_JULY_TUBE;
-  int odim = july ? 19 : 6;
+  int odim = obs_dim_of(c), ndim = node_dim_of(c);
   w->wi[GMPE_WI_STEP] += 1;
   for (int i = 0; i < N; ++i) set_action(w, i, act[w->b * N + i]);
   if (c->physics == GMPE_PHYS_FORCE) force_step(w); else kinematic_step(w, use_rk45);
@@ -895,15 +1180,16 @@ static void step_world(World* w, const int32_t* act, const GmpeStepInject* inj, 
   for (int i = 0; i < N; ++i) { /* env:1036-1053, agents in order */
     double otmp[19];
     double* o = out->obs ? (double*)out->obs + (w->b * N + i) * odim : otmp;
-    if (july) july_observation(w, i, o); else nav_observation(w, i, o);
+    scen_observation(w, i, o);
     double th = NAN;
     if (inj && inj->theta_draw) th = ((const double*)inj->theta_draw)[w->b * N + i];
     if (isnan(th))
       th = uni(c->seed, c->world_offset + w->b, (uint32_t)w->wi[GMPE_WI_EPISODE],
                (1u << 30) + (uint32_t)w->wi[GMPE_WI_STEP] * 64u + (uint32_t)i, 0, TWO_PI);
-    rew[i] = july ? july_reward(w, i, th) : nav_reward(w, i);
-    if (out->node_obs) node_features(w, i, (double*)out->node_obs + (w->b * N + i) * E * 8);
-    mask_adj(w);
+    rew[i] = c->scenario == GMPE_SCEN_JULY_TUBE ? july_reward(w, i, th)
+             : (c->scenario == GMPE_SCEN_THREE_PHASE ? tp_reward(w, i, th) : nav_reward(w, i));
+    if (out->node_obs) scen_node_features(w, i, (double*)out->node_obs + (w->b * N + i) * E * ndim);
+    scen_mask_adj(w);
     int done = w->fl[i * 4 + GMPE_AF_STATUS] || w->wi[GMPE_WI_STEP] >= c->episode_length; /* env:264-271 */
     out->done[w->b * N + i] = (uint8_t)done;
     all_done &= done;

@@ -169,7 +169,7 @@ def run_july_trace(path, seed, T, policy, eps=0.15, episodes=1, **over):
     rec = {k: [] for k in (
         "actions theta_draw state p_dist status prev_phase phase_reached goal_reached obs node_obs adj "
         "reward done info cnt delta_spacing_sum edge_index edge_attr num_edges "
-        "gnn_edge_index gnn_edge_attr gnn_num_edges").split()}
+        "gnn_edge_index gnn_edge_attr gnn_num_edges cooldown").split()}
     inits = {k: [] for k in "agent_state prev_phase tube landmarks obstacles goal_min_time reset_obs reset_node_obs reset_adj".split()}
 
     for ep in range(episodes):
@@ -216,6 +216,8 @@ def run_july_trace(path, seed, T, policy, eps=0.15, episodes=1, **over):
             rec["info"].append(np.array([[float(info_n[i][k]) for k in INFO_KEYS] for i in range(n)]))
             rec["cnt"].append(counters(env, sc))
             rec["delta_spacing_sum"].append(float(np.sum(sc.delta_spacing)))
+            # three_phase family: entry_reward_cooldown (three_phase_graph.py:348, 652-654, 1037)
+            rec["cooldown"].append(np.array(getattr(sc, "entry_reward_cooldown", np.zeros(n)), dtype=np.int64).copy())
             rec["edge_index"].append(ei); rec["edge_attr"].append(ea); rec["num_edges"].append(ne)
             rec["gnn_edge_index"].append(gei); rec["gnn_edge_attr"].append(gea); rec["gnn_num_edges"].append(gne)
 
@@ -228,7 +230,7 @@ def run_july_trace(path, seed, T, policy, eps=0.15, episodes=1, **over):
     np.savez_compressed(path, **out)
     st = out["status"]
     print(f"{os.path.basename(path)}: N={n} E={E} T={T}x{episodes} reached={int(st[-1].sum())} "
-          f"phases={sorted(set(out['obs'][..., 18].ravel().tolist()))} "
+          f"phases={sorted(set(out['obs'][..., -1].ravel().tolist()))} "
           f"rew[{out['reward'].min():.2f},{out['reward'].max():.2f}] size={os.path.getsize(path)//1024}KB")
 
 
@@ -311,6 +313,11 @@ def main():
     from multiagent.config import UnicycleVehicleConfig
     UnicycleVehicleConfig.COORDINATION_RANGE = UnicycleVehicleConfig.COMMUNICATION_RANGE
     run_july_trace(g("july_n3_unicycle_s9.npz"), seed=9, T=120, policy="pursuit", dynamics_type="unicycle_vehicle")
+    # rotation-invariant family: three_phase_graph.py, air_taxi, N = 3
+    run_july_trace(g("three_phase_n3_pursuit_s21.npz"), seed=21, T=150, policy="pursuit", scenario_name="three_phase_graph")
+    run_july_trace(g("three_phase_n3_pursuit_s22_ep2.npz"), seed=22, T=110, policy="pursuit", eps=0.3, episodes=2,
+                   scenario_name="three_phase_graph")
+    run_july_trace(g("three_phase_n3_random_s23.npz"), seed=23, T=60, policy="random", scenario_name="three_phase_graph")
     # stage-1 force physics: the live classic-MPE World.step
     run_classic_trace(g("classic_spread_n3_s11.npz"), seed=11, T=120)
     run_classic_trace(g("classic_spread_n6_s12.npz"), seed=12, T=80, num_agents=6, num_landmarks=6)

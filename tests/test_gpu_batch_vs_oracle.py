@@ -30,6 +30,11 @@ CASES = {
     "nav_n5_quirk": dict(args=dict(scenario_name="navigation_graph", num_agents=5, num_landmarks=6,
                                    num_obstacles=3, num_walls=4, world_size=2, episode_length=8), B=130, T=12,
                          kw=dict(wall_point_quirk=True)),
+    "three_phase_n3": dict(args=dict(scenario_name="three_phase_graph", dynamics_type="air_taxi", world_size=3,
+                                     episode_length=12, goal_rew=30, collaborative=False), B=1000, T=30),
+    "three_phase_n3_collab_unicycle": dict(args=dict(scenario_name="three_phase_graph", dynamics_type="unicycle_vehicle",
+                                                     world_size=3, episode_length=9, goal_rew=30, collaborative=True),
+                                           B=300, T=20),
     "july_di_kinematic": dict(args=dict(scenario_name="nav_metered_one_goal_graph_rotate_tube_july",
                                         dynamics_type="double_integrator", world_size=3, episode_length=12,
                                         goal_rew=30, collaborative=False, total_actions=9), B=200, T=20),
@@ -81,15 +86,18 @@ def test_fp64_free_running_with_auto_reset(case):
         fragile = (np.abs(pd - np.round(pd)) < 1e-9).any(axis=1)
         keep = ~fragile
         for k in REAL_OUT:
+            # three_phase features are float32-rounded values: a last-bit difference before the
+            # cast can round the other way (one float32 ulp)
+            tol = 1e-6 if (case.startswith("three_phase") and k in ("obs", "node_obs")) else 1e-9
             if k == "info":
                 _cmp_real(g[k][torch.as_tensor(keep, device="cuda")], o[k][keep], 1e-9, f"{case} t={t} {k}")
             else:
-                _cmp_real(g[k], o[k], 1e-9, f"{case} t={t} {k}")
+                _cmp_real(g[k], o[k], tol, f"{case} t={t} {k}")
         for k in INT_OUT:
             assert (g[k].cpu().numpy() == o[k]).all(), f"{case} t={t} {k}"
         for k in ("agent_state", "agent_aux", "world_f", "landmarks", "obstacles", "walls"):
             _cmp_real(eng.state[k], orc.state[k], 1e-9, f"{case} t={t} state.{k}")
-        for k in ("agent_flags", "world_i"):
+        for k in ("agent_flags", "world_i", "agent_ext"):
             assert (eng.state[k].cpu().numpy() == orc.state[k]).all(), f"{case} t={t} state.{k}"
         assert (eng.state["agent_cnt"].cpu().numpy()[keep] == orc.state["agent_cnt"][keep]).all(), f"{case} t={t} cnt"
         if fragile.any():  # re-synchronise the truncated counters of the fragile worlds
