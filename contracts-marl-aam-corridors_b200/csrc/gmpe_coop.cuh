@@ -43,8 +43,9 @@ namespace gmpe {
 template <typename Real, int SCEN, int N>
 struct CoopTraits {
   static constexpr int E = 2 * N, EE = E * E, CAP = E * (E - 1);
-  static constexpr int F = SCEN == GMPE_SCEN_JULY_TUBE ? 19 : (SCEN == GMPE_SCEN_THREE_PHASE ? 15 : 6);
-  static constexpr int ND = SCEN == GMPE_SCEN_THREE_PHASE ? 7 : 8;  // node feature width
+  static constexpr bool ROT_INV = SCEN == GMPE_SCEN_THREE_PHASE || SCEN == GMPE_SCEN_TWO_PHASE;
+  static constexpr int F = SCEN == GMPE_SCEN_JULY_TUBE ? 19 : (ROT_INV ? 15 : 6);
+  static constexpr int ND = ROT_INV ? 7 : 8;  // node feature width
   static constexpr int R = (int)sizeof(Real);
   static constexpr int WPW = 32 / N;   // worlds per warp
   static constexpr int AL = WPW * N;   // active lanes
@@ -98,7 +99,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
   using T = CoopTraits<Real, SCEN, N>;
   constexpr int E = T::E, EE = T::EE, CAP = T::CAP, F = T::F, WPW = T::WPW, AL = T::AL;
   constexpr bool july = SCEN == GMPE_SCEN_JULY_TUBE;
-  constexpr bool tp = SCEN == GMPE_SCEN_THREE_PHASE;  // three_phase_graph.py ("tp" in the citations)
+  constexpr bool tp2 = SCEN == GMPE_SCEN_TWO_PHASE;          // two_phase_graph.py ("tp2"): a variant of ...
+  constexpr bool tp = SCEN == GMPE_SCEN_THREE_PHASE || tp2;  // ... three_phase_graph.py ("tp" in the citations)
   constexpr bool tube = july || tp;                   // scenarios with a tube frame in world_f
   constexpr int ND = T::ND;
   extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -263,10 +265,11 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       } else if (tp) {
         Real ts, ty;
         tp_tube_coords<Real>(wf, s.x, s.y, ts, ty);
-        ph = tp_phase<Real>(ts, ty, wf[GMPE_WF_L], wf[GMPE_WF_HALF_W], pp, pr);
+        ph = tp_phase<Real, tp2>(ts, ty, wf[GMPE_WF_L], wf[GMPE_WF_HALF_W], pp, pr);
         cool -= cool > 0;  // get_agent_phase counts the cooldown down on every call (tp:652-654):
         cool -= cool > 0;  // once from observation(), once from reward()
-        reach = (ph == 2) && (d_goal < thr_goal) && !st_pre;  // tp:1110-1119
+        if (tp2) reach = (ph == 2) && (ph == pp + 1) && (pr == 1) && !st_pre;  // tp2:1036-1044: leaving through the exit gate
+        else reach = (ph == 2) && (d_goal < thr_goal) && !st_pre;             // tp:1110-1119
       } else {
         reach = (d_goal < thr_goal) && (c.flags & GMPE_FLAG_USE_DONES) && !st_pre;
       }
@@ -345,8 +348,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         pp = cur;
         rew = clip(rew, -Real(4) * coll, goal * Real(5));
         rew = clip(rew, Real(c.min_reward), Real(c.max_reward));
-      } else if (tp) {  // Scenario.reward (tp:957-1159)
-        rew -= Real(ncoll_rew) * coll;
+      } else if (tp) {  // Scenario.reward (tp:957-1159, tp2:955-1140)
+        if (!tp2) rew -= Real(ncoll_rew) * coll;  // commented out in tp2:962-970
         Real ts, ty;
         tp_tube_coords<Real>(wf, s.x, s.y, ts, ty);
         const Real L = wf[GMPE_WF_L], hw = wf[GMPE_WF_HALF_W];
@@ -354,7 +357,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         if (ph == 2 && ph > pp + 1) rew -= goal;  // tp:1018-1019
         if (ph == pp + 1 && pr == ph - 1) {       // tp:1028-1042
           if (ph == 1 && tp_in_entrance_gate(ts, ty, L, hw) && cool == 0) { rew += goal; cool = c.episode_length; pr = 1; }
-          else if (ph == 2) { rew += goal; pr = 2; }
+          else if (ph == 2) { rew += goal; pr = 2; if (tp2 && reach) rew += goal * Real(5); }
         }
         // |heading error| to the corridor axis: sin / cos of (theta - corridor_heading) from the unit vectors
         const Real ex_ = wf[GMPE_WF_E_X], ey_ = wf[GMPE_WF_E_Y];
@@ -371,7 +374,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
           rew -= tp_exit_gate_distance(ts, ty, L, hw);
           cnt[GMPE_AC_STEPS_IN_CORRIDOR] += 1;
           rew -= he * Real(c.formation_rew) * Real(0.1);
-        } else {  // tp:1110-1123
+        } else if (!tp2) {  // tp:1110-1123 (tp2 has no post-tube term)
           if (d_goal < thr_goal) { if (reach) rew += goal * Real(5); }
           else rew -= d_goal;
         }
@@ -380,7 +383,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         if (ph < pp) rew -= coll;
         if (ph < pr) rew -= coll;
         pp = ph;
-        if (tp_in_tube_rect(ts, ty, L, hw) && ph != 1 && !valid_exit) rew -= coll;  // tp:1145-1147
+        if (tp_in_tube_rect(ts, ty, L, hw) && ph != 1 && (tp2 || !valid_exit)) rew -= coll;  // tp:1145-1147, tp2:1130-1132
         if (ts > L && pr < 1) rew -= goal;                                           // tp:1149-1151
         rew = clip(rew, -Real(4) * coll, goal * Real(5));
       } else {
@@ -429,7 +432,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
           const bool nw_ = k <= i;
           cd[k] = Real(nw_ ? n0 : o0); ct[k] = Real(nw_ ? n1 : o1);
           dm += cd[k]; tm += ct[k]; sv += Real(nw_ ? n2 : o2);
-          if (nw_) dsum += spk;
+          if (nw_ && !tp2) dsum += spk;  // tp2 never appends to delta_spacing
         }
         dm = qdiv(dm, Real(N)); tm = qdiv(tm, Real(N));
         Real ds = Real(0), ts = Real(0);
@@ -537,7 +540,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       if (tp) {  // phase_reached and the cooldown were cleared by reset_world (tp:346-348)
         Real ts, ty;
         tp_tube_coords<Real>(wf, s.x, s.y, ts, ty);
-        ph_obs = tp_phase<Real>(ts, ty, wf[GMPE_WF_L], wf[GMPE_WF_HALF_W], pp, 0);
+        ph_obs = tp_phase<Real, tp2>(ts, ty, wf[GMPE_WF_L], wf[GMPE_WF_HALF_W], pp, 0);
         p.st.agent_ext[ga * 2] = 0;
         p.st.agent_ext[ga * 2 + 1] = 0;
       }
@@ -671,7 +674,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         o[0] = trunc32(hx); o[1] = trunc32(hy);
         o[2] = trunc32(spd_obs);
         Real ax, ay;
-        rot_into(hx, hy, lmi.x - s.x, lmi.y - s.y, ax, ay);
+        if (tp2) rot_into(hx, hy, trunc32(wf[GMPE_WF_EXIT_X]) - s.x, trunc32(wf[GMPE_WF_EXIT_Y]) - s.y, ax, ay);  // tp2:1196-1198
+        else rot_into(hx, hy, lmi.x - s.x, lmi.y - s.y, ax, ay);
         o[3] = trunc32(ax); o[4] = trunc32(ay);
         rot_into(hx, hy, trunc32(r1.x), trunc32(r1.y), ax, ay);  // float32 cast BEFORE the rotation (tp:1199)
         o[5] = trunc32(ax); o[6] = trunc32(ay);
@@ -719,7 +723,10 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         Real f[7];
         rot_into(hpx, hpy, trunc32(vkx - vex), trunc32(vky - vey), f[0], f[1]);
         rot_into(hpx, hpy, trunc32(pkx - pex), trunc32(pky - pey), f[2], f[3]);
-        if (k < N) rot_into(hpx, hpy, trunc32(trunc32(LX[k]) - pex), trunc32(trunc32(LY[k]) - pey), f[4], f[5]);
+        if (k < N) {
+          const Real gx = tp2 ? trunc32(wf[GMPE_WF_EXIT_X]) : trunc32(LX[k]), gy = tp2 ? trunc32(wf[GMPE_WF_EXIT_Y]) : trunc32(LY[k]);  // tp2:1405
+          rot_into(hpx, hpy, trunc32(gx - pex), trunc32(gy - pey), f[4], f[5]);
+        }
         else { f[4] = f[2]; f[5] = f[3]; }
         f[6] = k < N ? Real(0) : Real(1);
 #pragma unroll

@@ -299,13 +299,17 @@ __device__ __forceinline__ Real tp_exit_gate_distance(Real s, Real y, Real L, Re
   return hypot_(ds, y - clip(y, -hw, hw));
 }
 // get_agent_phase (tp:639-705); previous_phase / phase_reached are only read
-template <typename Real>
+// two_phase_graph.py ("tp2", TWO = true) lacks the "previous_phase == 2 and valid_exit" branch
+// (tp:681-683 vs tp2:676-681); where tp2 falls off the end and returns None (an agent beyond the
+// exit plane that never entered: float(None) raises in the reference) this build returns 0.
+template <typename Real, bool TWO>
 __device__ __forceinline__ int tp_phase(Real s, Real y, Real L, Real hw, int pp, int pr) {
   const bool in_tube = tp_in_tube_rect(s, y, L, hw), passed = s > L;
   const bool valid_exit = tp_in_exit_gate(s, y, L, hw);
   if (!in_tube && !passed) return 0;
   if (in_tube) {
     if (pp == 0) return tp_in_entrance_gate(s, y, L, hw) ? 1 : 0;
+    if (TWO) return (pp == 1 && valid_exit) ? 2 : 1;
     return valid_exit ? 2 : 1;  // pp is 1 or 2 here
   }
   if (pr >= 1) {  // passed the exit plane

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GMPE_ABI_VERSION 7
+#define GMPE_ABI_VERSION 8
 
 /* error codes */
 #define GMPE_OK 0
@@ -42,6 +42,9 @@ extern "C" {
 #define GMPE_SCEN_THREE_PHASE 2 /* three_phase_graph.py: rotation-invariant fp32 features, 15-d obs,
                                    7-d nodes, exit gate, random tube length;
                                    served for N = L = 3, O = W = 0 */
+#define GMPE_SCEN_TWO_PHASE 3 /* two_phase_graph.py (eval_scripts/commands_test_run.txt:14): the same family;
+                                 the goal is the tube exit -- an agent is done when it leaves through the
+                                 exit gate; no agent-collision penalty; same layouts and restrictions */
 /* GmpeConfig.dynamics -- multiagent/core.py:23-26 EntityDynamicsType */
 #define GMPE_DYN_DOUBLE_INTEGRATOR 0
 #define GMPE_DYN_UNICYCLE 1
@@ -166,8 +169,8 @@ typedef struct GmpeConfig {
 typedef struct GmpeLayout {
   int32_t real_bytes;   /* 4 or 8 */
   int32_t num_entities; /* E = N+L+O+W */
-  int32_t obs_dim;      /* F_obs: 19 july, 6 nav, 15 three_phase */
-  int32_t node_dim;     /* F_node: 8 (7 three_phase) */
+  int32_t obs_dim;      /* F_obs: 19 july, 6 nav, 15 two/three_phase */
+  int32_t node_dim;     /* F_node: 8 (7 two/three_phase) */
   int32_t edge_cap;     /* E*(E-1) */
   int32_t info_dim;     /* GMPE_INFO_K */
   int64_t agent_state, agent_aux, agent_flags, agent_cnt;
@@ -189,7 +192,7 @@ typedef struct GmpeState {
   void* obstacles;      /* Real [B][O][2]  (may be NULL when O == 0)                                   */
   void* walls;          /* Real [B][W][GMPE_WALL_F] (may be NULL when W == 0)                          */
   int32_t* agent_ext;   /* i32  [B][N][2]: entry_reward_cooldown (three_phase_graph.py:348,652-654,1037),
-                           spare.  GMPE_SCEN_THREE_PHASE only; may be NULL for the other scenarios      */
+                           spare.  GMPE_SCEN_THREE_PHASE / TWO_PHASE only; may be NULL for the other scenarios      */
 } GmpeState;
 
 /* Per-step outputs (device pointers, caller-owned).  Any pointer may be NULL to

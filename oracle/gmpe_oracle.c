@@ -680,6 +680,7 @@ static void july_info(World* w, int i, double* info) {
  * (SURVEY 8f rank 3).  reset_world / info_callback / is_collision / min_time are identical to
  * july (diff of tp:315-399, 723-815, 847-956 against july:339-420, 741-829, 864-973 is empty up
  * to a float32 cast and one extra info key), so those are shared. */
+static int is_two_phase(const World* w) { return w->c->scenario == GMPE_SCEN_TWO_PHASE; } /* two_phase_graph.py ("tp2") */
 static double agent_theta(const World* w, int i) { /* state.theta; arctan2(vy, vx) for the DI (core:188-189) */
   const double* s = w->as + i * 4;
   return is_kin_heading(w->c) ? s[2] : atan2(s[3], s[2]);
@@ -729,9 +730,11 @@ static int tp_get_agent_phase(World* w, int i) {
   if (in_tube) {
     if (pp == 0) return valid_entrance ? 1 : 0;
     if (pp == 1 && valid_exit) return 2;
-    if (pp == 2 && valid_exit) return 2;
+    if (pp == 2 && valid_exit && !is_two_phase(w)) return 2; /* tp:681-683; absent from tp2:676-681 */
     return 1;
   }
+  /* tp2 falls off the end (returns None -> float(None) raises) when an agent passes the exit
+   * plane without ever having entered; this build returns 0 there like tp:704 */
   if (passed && w->fl[i * 4 + GMPE_AF_PHASE_REACHED] >= 1) {
     if (pp == 1 && valid_exit) return 2;
     if (pp == 2) return 2;
@@ -746,7 +749,9 @@ static void tp_observation(World* w, int i, double* o) {
   double h = agent_theta(w, i);
   double speed = is_kin_heading(w->c) ? p[3] : norm2(p[2], p[3]);
   double g[2];
-  rot_rel(h, w->lm[i * 2] - p[0], w->lm[i * 2 + 1] - p[1], g); /* goal_match_index = arange (tp:325) */
+  if (is_two_phase(w)) /* tp2:1196-1198: the goal slot holds the float32 tube exit, rotated */
+    rot_rel(h, (double)(float)w->wf[GMPE_WF_EXIT_X] - p[0], (double)(float)w->wf[GMPE_WF_EXIT_Y] - p[1], g);
+  else rot_rel(h, w->lm[i * 2] - p[0], w->lm[i * 2 + 1] - p[1], g); /* goal_match_index = arange (tp:325) */
   double nd[MAXN], nr[MAXN][2];
   int order[MAXN], m = 0;
   for (int k = 0; k < w->N; ++k) { /* tp:1182-1191: done agents are not neighbours */
@@ -784,7 +789,7 @@ static double tp_reward(World* w, int i, double theta_draw) {
   double* st = w->as + i * 4;
   uint8_t* fl = w->fl + i * 4;
   int32_t* cnt = w->cnt + i * GMPE_AGENT_CNT;
-  for (int a = 0; a < w->N; ++a) { /* tp:965-970 */
+  for (int a = 0; a < w->N && !is_two_phase(w); ++a) { /* tp:965-970; commented out in tp2:962-970 */
     if (a == i) continue;
     if (is_collision(w, a, i)) rew -= c->collision_rew;
   }
@@ -811,6 +816,12 @@ static double tp_reward(World* w, int i, double theta_draw) {
     } else if (phase == 2) {
       rew += c->goal_rew;
       fl[GMPE_AF_PHASE_REACHED] = 2;
+      if (is_two_phase(w) && !fl[GMPE_AF_STATUS]) { /* tp2:1041-1044: leaving through the exit gate IS the goal */
+        fl[GMPE_AF_STATUS] = 1;
+        if (is_kin_heading(c)) { st[2] = theta_draw; st[3] = c->v_min; }
+        else { st[2] = 0; st[3] = 0; }
+        rew += c->goal_rew * 5;
+      }
     }
   }
   double corridor_heading = atan2(w->wf[GMPE_WF_E_Y], w->wf[GMPE_WF_E_X]);
@@ -833,10 +844,10 @@ static double tp_reward(World* w, int i, double theta_draw) {
     rew -= spacing_error * c->formation_rew;
     rew -= tp_exit_gate_distance(s, y, L, hw);
     cnt[GMPE_AC_STEPS_IN_CORRIDOR] += 1;
-    w->wf[GMPE_WF_DELTA_SPACING] += spacing_error;
+    if (!is_two_phase(w)) w->wf[GMPE_WF_DELTA_SPACING] += spacing_error; /* tp:1101; not in tp2 */
     double he = fabs(pymod2pi(theta - corridor_heading + PI_D) - PI_D);
     rew -= he * c->formation_rew * 0.1;
-  } else if (phase == 2) { /* tp:1110-1123; goal_tracker is NOT updated here (line commented out) */
+  } else if (phase == 2 && !is_two_phase(w)) { /* tp:1110-1123; goal_tracker is NOT updated here (line commented out) */
     double d = norm2(st[0] - w->lm[i * 2], st[1] - w->lm[i * 2 + 1]);
     if (d < c->goal_dist_thresh) {
       if (!fl[GMPE_AF_STATUS]) {
@@ -852,7 +863,7 @@ static double tp_reward(World* w, int i, double theta_draw) {
   if (phase < fl[GMPE_AF_PREV_PHASE]) rew -= c->collision_rew;
   if (phase < fl[GMPE_AF_PHASE_REACHED]) rew -= c->collision_rew;
   fl[GMPE_AF_PREV_PHASE] = (uint8_t)phase;
-  if (tp_in_tube_rect(s, y, L, hw) && phase != 1 && !valid_exit) rew -= c->collision_rew; /* tp:1145-1147 */
+  if (tp_in_tube_rect(s, y, L, hw) && phase != 1 && (is_two_phase(w) || !valid_exit)) rew -= c->collision_rew; /* tp:1145-1147, tp2:1130-1132 */
   if (s > L && fl[GMPE_AF_PHASE_REACHED] < 1) rew -= c->goal_rew;                             /* tp:1149-1151 */
   return clipd(rew, -4 * c->collision_rew, c->goal_rew * 5);
 }
@@ -877,6 +888,7 @@ static void tp_node_features(World* w, int ego, double* out /* [E][7] */) {
     rot_rel(h, (double)(float)(vk[0] - ve[0]), (double)(float)(vk[1] - ve[1]), rv);
     if (k < w->N) {
       float gx = (float)w->lm[k * 2], gy = (float)w->lm[k * 2 + 1]; /* landmark_poses[goal_match_index[entity.id]] */
+      if (is_two_phase(w)) { gx = (float)w->wf[GMPE_WF_EXIT_X]; gy = (float)w->wf[GMPE_WF_EXIT_Y]; } /* tp2:1405 */
       rot_rel(h, (double)(float)(gx - pe[0]), (double)(float)(gy - pe[1]), rg);
     } else { rg[0] = rp[0]; rg[1] = rp[1]; }
     double* f = out + k * 7;
@@ -1125,20 +1137,21 @@ static void write_graph_outputs(World* w, const GmpeStepOut* out) {
 }
 
 /* MultiAgentGraphEnv.reset env:1066-1081 -> reset_world july:339-420 */
-static int obs_dim_of(const GmpeConfig* c) { return c->scenario == GMPE_SCEN_JULY_TUBE ? 19 : (c->scenario == GMPE_SCEN_THREE_PHASE ? 15 : 6); }
-static int node_dim_of(const GmpeConfig* c) { return c->scenario == GMPE_SCEN_THREE_PHASE ? 7 : 8; }
+static int rot_inv(const GmpeConfig* c) { return c->scenario == GMPE_SCEN_THREE_PHASE || c->scenario == GMPE_SCEN_TWO_PHASE; }
+static int obs_dim_of(const GmpeConfig* c) { return c->scenario == GMPE_SCEN_JULY_TUBE ? 19 : (rot_inv(c) ? 15 : 6); }
+static int node_dim_of(const GmpeConfig* c) { return rot_inv(c) ? 7 : 8; }
 static void scen_observation(World* w, int i, double* o) {
   switch (w->c->scenario) {
     case GMPE_SCEN_JULY_TUBE: july_observation(w, i, o); break;
-    case GMPE_SCEN_THREE_PHASE: tp_observation(w, i, o); break;
+    case GMPE_SCEN_THREE_PHASE: case GMPE_SCEN_TWO_PHASE: tp_observation(w, i, o); break;
     default: nav_observation(w, i, o);
   }
 }
 static void scen_node_features(World* w, int i, double* out) {
-  if (w->c->scenario == GMPE_SCEN_THREE_PHASE) tp_node_features(w, i, out); else node_features(w, i, out);
+  if (rot_inv(w->c)) tp_node_features(w, i, out); else node_features(w, i, out);
 }
 static void scen_mask_adj(World* w) {
-  if (w->c->scenario == GMPE_SCEN_THREE_PHASE) tp_mask_adj(w); else mask_adj(w);
+  if (rot_inv(w->c)) tp_mask_adj(w); else mask_adj(w);
 }
 
 static void reset_world(World* w, const GmpeStepInject* inj, const GmpeStepOut* out) {
@@ -1148,7 +1161,7 @@ static void reset_world(World* w, const GmpeStepInject* inj, const GmpeStepOut* 
   if (inj && inj->reset_state) adopt_injected(w, inj->reset_state);
   else {
     if (c->scenario == GMPE_SCEN_JULY_TUBE) july_random_scenario(w);
-    else if (c->scenario == GMPE_SCEN_THREE_PHASE) tp_random_scenario(w);
+    else if (rot_inv(c)) tp_random_scenario(w);
     else nav_random_scenario(w);
     for (int i = 0; i < w->N; ++i) /* min_time july:941-951 */
       w->aux[i * 2 + 1] = norm2(w->as[i * 4] - w->lm[i * 2], w->as[i * 4 + 1] - w->lm[i * 2 + 1]) / c->max_speed;
@@ -1158,7 +1171,7 @@ static void reset_world(World* w, const GmpeStepInject* inj, const GmpeStepOut* 
   for (int i = 0; i < w->N; ++i) {
     if (out->obs) scen_observation(w, i, (double*)out->obs + (w->b * w->N + i) * odim);
     else if (c->scenario == GMPE_SCEN_JULY_TUBE) (void)get_agent_phase(w, i);
-    else if (c->scenario == GMPE_SCEN_THREE_PHASE) (void)tp_get_agent_phase(w, i);
+    else if (rot_inv(c)) (void)tp_get_agent_phase(w, i);
     if (out->node_obs) scen_node_features(w, i, (double*)out->node_obs + (w->b * w->N + i) * w->E * ndim);
   }
   scen_mask_adj(w);
@@ -1187,7 +1200,7 @@ static void step_world(World* w, const int32_t* act, const GmpeStepInject* inj, 
       th = uni(c->seed, c->world_offset + w->b, (uint32_t)w->wi[GMPE_WI_EPISODE],
                (1u << 30) + (uint32_t)w->wi[GMPE_WI_STEP] * 64u + (uint32_t)i, 0, TWO_PI);
     rew[i] = c->scenario == GMPE_SCEN_JULY_TUBE ? july_reward(w, i, th)
-             : (c->scenario == GMPE_SCEN_THREE_PHASE ? tp_reward(w, i, th) : nav_reward(w, i));
+             : (rot_inv(c) ? tp_reward(w, i, th) : nav_reward(w, i));
     if (out->node_obs) scen_node_features(w, i, (double*)out->node_obs + (w->b * N + i) * E * ndim);
     scen_mask_adj(w);
     int done = w->fl[i * 4 + GMPE_AF_STATUS] || w->wi[GMPE_WI_STEP] >= c->episode_length; /* env:264-271 */

@@ -318,6 +318,10 @@ def main():
     run_july_trace(g("three_phase_n3_pursuit_s22_ep2.npz"), seed=22, T=110, policy="pursuit", eps=0.3, episodes=2,
                    scenario_name="three_phase_graph")
     run_july_trace(g("three_phase_n3_random_s23.npz"), seed=23, T=60, policy="random", scenario_name="three_phase_graph")
+    # ... and two_phase_graph.py (eval_scripts/commands_test_run.txt:14)
+    run_july_trace(g("two_phase_n3_pursuit_s31.npz"), seed=31, T=150, policy="pursuit", scenario_name="two_phase_graph")
+    run_july_trace(g("two_phase_n3_pursuit_s32_ep2.npz"), seed=32, T=110, policy="pursuit", eps=0.3, episodes=2,
+                   scenario_name="two_phase_graph")
     # stage-1 force physics: the live classic-MPE World.step
     run_classic_trace(g("classic_spread_n3_s11.npz"), seed=11, T=120)
     run_classic_trace(g("classic_spread_n6_s12.npz"), seed=12, T=80, num_agents=6, num_landmarks=6)
