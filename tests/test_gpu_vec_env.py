@@ -110,11 +110,13 @@ def test_vec_env_device_output_mode_is_zero_copy():
     envs.close()
 
 
-def test_multi_agent_graph_env_replays_a_golden_episode_through_the_scenario_api():
+@pytest.mark.parametrize("which", ["july_n3_pursuit_s1", "three_phase_n3_pursuit_s21", "two_phase_n3_pursuit_s31"])
+def test_multi_agent_graph_env_replays_a_golden_episode_through_the_scenario_api(which):
     from gmpe_b200.environment import MultiAgentGraphEnv
     from gmpe_b200.scenario import Scenario
 
-    tr = Trace([p for p in traces() if "n3_pursuit_s1" in p][0])
+    tr = Trace([p for p in traces("*.npz") if which in p][0])
+    F, ND, tol = (19, 8, 2e-7) if which.startswith("july") else (15, 7, 1e-6)
     scenario = Scenario(precision="fp64")
     world = scenario.make_world(tr.args)
     env = MultiAgentGraphEnv(world=world, reset_callback=scenario.reset_world, reward_callback=scenario.reward,
@@ -123,9 +125,9 @@ def test_multi_agent_graph_env_replays_a_golden_episode_through_the_scenario_api
                              id_callback=scenario.get_id, info_callback=scenario.info_callback,
                              done_callback=scenario.done, scenario_name=tr.args.scenario_name,
                              dynamics_type=tr.args.dynamics_type)
-    assert env.n == 3 and env.action_space[0].n == 25 and env.observation_space[0].shape == (19,)
+    assert env.n == 3 and env.action_space[0].n == 25 and env.observation_space[0].shape == (F,)
     obs_n, id_n, node_n, adj_n = env.reset()
-    assert len(obs_n) == 3 and node_n[0].shape == (6, 8) and adj_n[0].shape == (6, 6)
+    assert len(obs_n) == 3 and node_n[0].shape == (6, ND) and adj_n[0].shape == (6, 6)
     z = tr.z
     world.engine.reset(reset_state=tr.reset_state(0))  # teacher-forced initial condition of the trace
     world.engine.state["agent_flags"][0, :, abi.AF_PREV_PHASE] = torch.as_tensor(z["init_prev_phase"][0], dtype=torch.uint8)
@@ -134,10 +136,10 @@ def test_multi_agent_graph_env_replays_a_golden_episode_through_the_scenario_api
         if not np.isnan(z["theta_draw"][t]).all():
             break  # the B=1 env draws its own headings; stop before the first goal reach
         obs_n, id_n, node_n, adj_n, rew_n, done_n, info_n = env.step([np.eye(25)[a] for a in z["actions"][t]])
-        np.testing.assert_allclose(np.array(obs_n), z["obs"][t], atol=2e-7)
-        np.testing.assert_allclose(np.array(node_n), z["node_obs"][t], atol=2e-7)
+        np.testing.assert_allclose(np.array(obs_n), z["obs"][t], atol=tol)
+        np.testing.assert_allclose(np.array(node_n), z["node_obs"][t], atol=tol)
         np.testing.assert_allclose(adj_n[0], z["adj"][t], atol=2e-7)
-        np.testing.assert_allclose(np.array(rew_n), z["reward"][t], atol=2e-7)
+        np.testing.assert_allclose(np.array(rew_n), z["reward"][t], atol=tol)
         assert done_n == list(z["done"][t])
         assert info_n[1]["individual_reward"] == rew_n[1] and "Num_agent_collisions" in info_n[0]
         assert (world.edge_list == z["edge_index"][t][:, :z["num_edges"][t]]).all()
