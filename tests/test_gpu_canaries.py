@@ -19,6 +19,11 @@ CASES = {
                     episode_length=4, goal_rew=30, collaborative=False),
     "nav_n5_walls": dict(scenario_name="navigation_graph", num_agents=5, num_landmarks=6, num_obstacles=3, num_walls=4,
                          world_size=2, episode_length=4),
+    # GMPE_MAX_AGENTS agents and GMPE_MAX_ENTITIES entities
+    "nav_max_entities": dict(scenario_name="navigation_graph", num_agents=64, num_landmarks=64, num_obstacles=28, num_walls=4,
+                             world_size=14, episode_length=3),
+    "three_phase_n3": dict(scenario_name="three_phase_graph", dynamics_type="air_taxi", world_size=3, episode_length=4,
+                           goal_rew=30, collaborative=False),
     "july_n64": dict(scenario_name="nav_metered_one_goal_graph_rotate_tube_july", dynamics_type="air_taxi", num_agents=64,
                      num_landmarks=64, world_size=12, episode_length=3, goal_rew=30, collaborative=False),
 }
@@ -38,6 +43,8 @@ def test_kernels_never_write_outside_their_arrays(case, precision):
     from gmpe_b200.engine import BatchedGraphMPE
 
     B = 70 if CASES[case].get("num_agents", 3) < 64 else 5
+    if precision == "fp64" and case == "nav_max_entities":
+        B = 3
     cfg = make_config(default_args(**CASES[case]), B, precision=precision, seed=3, gnn_edges=True)
     ref = BatchedGraphMPE(cfg, 0)
     lib = ref.lib
