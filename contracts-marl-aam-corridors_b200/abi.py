@@ -10,13 +10,13 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # error codes
 OK, E_INVALID, E_CUDA, E_NULL = 0, -1, -2, -3
 
-SCEN_JULY_TUBE, SCEN_NAV_GRAPH, SCEN_THREE_PHASE, SCEN_TWO_PHASE = 0, 1, 2, 3
-ROT_INV_SCENARIOS = (SCEN_THREE_PHASE, SCEN_TWO_PHASE)
+SCEN_JULY_TUBE, SCEN_NAV_GRAPH, SCEN_THREE_PHASE, SCEN_TWO_PHASE, SCEN_CORRIDOR_ROT_INV = 0, 1, 2, 3, 4
+ROT_INV_SCENARIOS = (SCEN_THREE_PHASE, SCEN_TWO_PHASE, SCEN_CORRIDOR_ROT_INV)
 DYN_DOUBLE_INTEGRATOR, DYN_UNICYCLE, DYN_AIR_TAXI = 0, 1, 2
 PHYS_KINEMATIC, PHYS_FORCE = 0, 1
 F32, F64 = 0, 1
@@ -177,7 +177,7 @@ def layout_for(cfg: GmpeConfig) -> GmpeLayout:
     E = N + L + O + W
     lay.real_bytes = 8 if cfg.precision == F64 else 4
     lay.num_entities = E
-    lay.obs_dim = {SCEN_JULY_TUBE: 19, SCEN_NAV_GRAPH: 6, SCEN_THREE_PHASE: 15, SCEN_TWO_PHASE: 15}[cfg.scenario]
+    lay.obs_dim = {SCEN_JULY_TUBE: 19, SCEN_NAV_GRAPH: 6, SCEN_THREE_PHASE: 15, SCEN_TWO_PHASE: 15, SCEN_CORRIDOR_ROT_INV: 13}[cfg.scenario]
     lay.node_dim = 7 if cfg.scenario in ROT_INV_SCENARIOS else 8
     lay.edge_cap = E * (E - 1)
     lay.info_dim = INFO_K

@@ -72,6 +72,7 @@ JULY_SCENARIOS = ("nav_metered_one_goal_graph_rotate_tube_july",)
 NAV_SCENARIOS = ("navigation_graph",)
 THREE_PHASE_SCENARIOS = ("three_phase_graph",)
 TWO_PHASE_SCENARIOS = ("two_phase_graph",)
+CORRIDOR_ROT_INV_SCENARIOS = ("nav_graph_metered_single_corridor_rot_inv",)
 
 
 def default_args(**over) -> SimpleNamespace:
@@ -112,9 +113,11 @@ def make_config(args, num_worlds: int, *, precision: str = "fp32", seed: int | N
         scen = abi.SCEN_THREE_PHASE
     elif name in TWO_PHASE_SCENARIOS:
         scen = abi.SCEN_TWO_PHASE
+    elif name in CORRIDOR_ROT_INV_SCENARIOS:
+        scen = abi.SCEN_CORRIDOR_ROT_INV
     else:
-        raise ValueError(f"scenario {name!r} is not served by this build "
-                         f"(have {JULY_SCENARIOS + NAV_SCENARIOS + THREE_PHASE_SCENARIOS + TWO_PHASE_SCENARIOS})")
+        raise ValueError(f"scenario {name!r} is not served by this build (have "
+                         f"{JULY_SCENARIOS + NAV_SCENARIOS + THREE_PHASE_SCENARIOS + TWO_PHASE_SCENARIOS + CORRIDOR_ROT_INV_SCENARIOS})")
     if args.dynamics_type not in DYNAMICS:
         raise NotImplementedError(args.dynamics_type)  # environment.py:77-78
     dyn, K = DYNAMICS[args.dynamics_type]
@@ -200,9 +203,9 @@ def validate(c: abi.GmpeConfig) -> None:
     if L < N:
         raise ValueError("num_landmarks must be >= num_agents (landmark_poses[agent.id], july:1740)")
     if c.scenario in abi.ROT_INV_SCENARIOS and not (N == 3 and L == 3 and O == 0 and W == 0):
-        raise ValueError("two/three_phase_graph are served for num_agents == num_landmarks == 3 without obstacles / walls")
+        raise ValueError("the rot-inv scenarios are served for num_agents == num_landmarks == 3 without obstacles / walls")
     if c.scenario in abi.ROT_INV_SCENARIOS and c.physics != abi.PHYS_KINEMATIC:
-        raise ValueError("two/three_phase_graph use the kinematic step")
+        raise ValueError("the rot-inv scenarios use the kinematic step")
     if c.scenario == abi.SCEN_JULY_TUBE and (O or W):
         # the reference graph builder raises for obstacles / walls in this scenario
         raise ValueError("the july tube scenario supports num_obstacles == num_walls == 0 only")

@@ -38,8 +38,12 @@ static int fail(gmpe_ctx* h, int code, const std::string& msg) {
   return code;
 }
 
-static bool rot_inv(const GmpeConfig& c) { return c.scenario == GMPE_SCEN_THREE_PHASE || c.scenario == GMPE_SCEN_TWO_PHASE; }
-static int obs_dim_of(const GmpeConfig& c) { return c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : (rot_inv(c) ? 15 : 6); }
+static bool rot_inv(const GmpeConfig& c) {
+  return c.scenario == GMPE_SCEN_THREE_PHASE || c.scenario == GMPE_SCEN_TWO_PHASE || c.scenario == GMPE_SCEN_CORRIDOR_ROT_INV;
+}
+static int obs_dim_of(const GmpeConfig& c) {
+  return c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : (c.scenario == GMPE_SCEN_CORRIDOR_ROT_INV ? 13 : (rot_inv(c) ? 15 : 6));
+}
 static int node_dim_of(const GmpeConfig& c) { return rot_inv(c) ? 7 : 8; }
 
 static const char* validate(const GmpeConfig& c) {
@@ -54,7 +58,7 @@ static const char* validate(const GmpeConfig& c) {
   if (c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls > GMPE_MAX_ENTITIES) return "too many entities";
   if (rot_inv(c) &&
       !(c.num_agents == 3 && c.num_landmarks == 3 && c.num_obstacles == 0 && c.num_walls == 0 && c.physics == GMPE_PHYS_KINEMATIC))
-    return "two/three_phase_graph are served for num_agents == num_landmarks == 3 without obstacles / walls, kinematic step";
+    return "the rot-inv scenarios are served for num_agents == num_landmarks == 3 without obstacles / walls, kinematic step";
   if (c.scenario == GMPE_SCEN_JULY_TUBE && (c.num_obstacles || c.num_walls))
     return "july tube scenario supports num_obstacles == num_walls == 0 only (the reference graph builder raises, SURVEY G7)";
   if (c.physics == GMPE_PHYS_FORCE && c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR) return "force physics needs double_integrator state";
@@ -250,6 +254,9 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
       } else if (sc == GMPE_SCEN_TWO_PHASE) {                                                             \
         h->fn = (const void*)gmpe_step_coop_kernel<REAL, GMPE_SCEN_TWO_PHASE, 3>;                         \
         h->smem_bytes = GMPE_COOP_WARPS * CoopTraits<REAL, GMPE_SCEN_TWO_PHASE, 3>::SLAB_BYTES;           \
+      } else if (sc == GMPE_SCEN_CORRIDOR_ROT_INV) {                                                      \
+        h->fn = (const void*)gmpe_step_coop_kernel<REAL, GMPE_SCEN_CORRIDOR_ROT_INV, 3>;                  \
+        h->smem_bytes = GMPE_COOP_WARPS * CoopTraits<REAL, GMPE_SCEN_CORRIDOR_ROT_INV, 3>::SLAB_BYTES;    \
       } else {                                                                                            \
         h->fn = (const void*)gmpe_step_coop_kernel<REAL, GMPE_SCEN_NAV_GRAPH, 3>;                         \
         h->smem_bytes = GMPE_COOP_WARPS * CoopTraits<REAL, GMPE_SCEN_NAV_GRAPH, 3>::SLAB_BYTES;           \
@@ -381,7 +388,7 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   if (!st->agent_state || !st->agent_aux || !st->agent_flags || !st->agent_cnt || !st->world_f || !st->world_i || !st->landmarks)
     return fail(h, GMPE_E_NULL, "a required state array is NULL");
   if ((c.num_obstacles && !st->obstacles) || (c.num_walls && !st->walls)) return fail(h, GMPE_E_NULL, "obstacles / walls array is NULL");
-  if (rot_inv(c) && !st->agent_ext) return fail(h, GMPE_E_NULL, "two/three_phase_graph need state.agent_ext");
+  if (rot_inv(c) && !st->agent_ext) return fail(h, GMPE_E_NULL, "the rot-inv scenarios need state.agent_ext");
   if (mode == MODE_STEP && (!act || !out->reward || !out->done)) return fail(h, GMPE_E_NULL, "gmpe_step needs action_idx, out.reward and out.done");
   if ((c.flags & GMPE_FLAG_ENV_EDGES) && out->edge_index && (!out->edge_attr || !out->num_edges)) return fail(h, GMPE_E_NULL, "edge_attr / num_edges missing");
   if ((c.flags & GMPE_FLAG_GNN_EDGES) && out->gnn_edge_index && (!out->gnn_edge_attr || !out->gnn_num_edges)) return fail(h, GMPE_E_NULL, "gnn_edge_attr / gnn_num_edges missing");

@@ -43,8 +43,8 @@ namespace gmpe {
 template <typename Real, int SCEN, int N>
 struct CoopTraits {
   static constexpr int E = 2 * N, EE = E * E, CAP = E * (E - 1);
-  static constexpr bool ROT_INV = SCEN == GMPE_SCEN_THREE_PHASE || SCEN == GMPE_SCEN_TWO_PHASE;
-  static constexpr int F = SCEN == GMPE_SCEN_JULY_TUBE ? 19 : (ROT_INV ? 15 : 6);
+  static constexpr bool ROT_INV = SCEN == GMPE_SCEN_THREE_PHASE || SCEN == GMPE_SCEN_TWO_PHASE || SCEN == GMPE_SCEN_CORRIDOR_ROT_INV;
+  static constexpr int F = SCEN == GMPE_SCEN_JULY_TUBE ? 19 : (SCEN == GMPE_SCEN_CORRIDOR_ROT_INV ? 13 : (ROT_INV ? 15 : 6));
   static constexpr int ND = ROT_INV ? 7 : 8;  // node feature width
   static constexpr int R = (int)sizeof(Real);
   static constexpr int WPW = 32 / N;   // worlds per warp
@@ -100,7 +100,9 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
   constexpr int E = T::E, EE = T::EE, CAP = T::CAP, F = T::F, WPW = T::WPW, AL = T::AL;
   constexpr bool july = SCEN == GMPE_SCEN_JULY_TUBE;
   constexpr bool tp2 = SCEN == GMPE_SCEN_TWO_PHASE;          // two_phase_graph.py ("tp2"): a variant of ...
-  constexpr bool tp = SCEN == GMPE_SCEN_THREE_PHASE || tp2;  // ... three_phase_graph.py ("tp" in the citations)
+  constexpr bool sc = SCEN == GMPE_SCEN_CORRIDOR_ROT_INV;    // nav_graph_metered_single_corridor_rot_inv.py ("sc"): another
+  constexpr bool tp = SCEN == GMPE_SCEN_THREE_PHASE || tp2 || sc;  // ... three_phase_graph.py ("tp" in the citations)
+  constexpr int TPV = tp2 ? 1 : (sc ? 2 : 0);
   constexpr bool tube = july || tp;                   // scenarios with a tube frame in world_f
   constexpr int ND = T::ND;
   extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -152,8 +154,10 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     int st_pre = flw & 0xff, pp = (flw >> 8) & 0xff, pr = (flw >> 16) & 0xff, gr = (flw >> 24) & 0xff;
     Real wf[12];
     Real dsum0 = Real(0);
-    int cool = 0;  // tp: entry_reward_cooldown (tp:348)
+    int cool = 0;          // tp: entry_reward_cooldown (tp:348)
+    float prev_proj = 0;   // sc: prev_proj, a float32 array (sc:374)
     if (tp) cool = p.st.agent_ext[ga * 2];
+    if (sc) prev_proj = __int_as_float(p.st.agent_ext[ga * 2 + 1]);
     if (tube) {
       const Real* gw_ = g_wf + (size_t)b * GMPE_WORLD_F;
 #pragma unroll
@@ -265,10 +269,11 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       } else if (tp) {
         Real ts, ty;
         tp_tube_coords<Real>(wf, s.x, s.y, ts, ty);
-        ph = tp_phase<Real, tp2>(ts, ty, wf[GMPE_WF_L], wf[GMPE_WF_HALF_W], pp, pr);
+        ph = tp_phase<Real, TPV>(ts, ty, wf[GMPE_WF_L], wf[GMPE_WF_HALF_W], pp, pr);
         cool -= cool > 0;  // get_agent_phase counts the cooldown down on every call (tp:652-654):
         cool -= cool > 0;  // once from observation(), once from reward()
         if (tp2) reach = (ph == 2) && (ph == pp + 1) && (pr == 1) && !st_pre;  // tp2:1036-1044: leaving through the exit gate
+        else if (sc) reach = (ph == 2) && (pr != 0) && (d_goal < thr_goal) && !st_pre;  // sc:1278-1294
         else reach = (ph == 2) && (d_goal < thr_goal) && !st_pre;             // tp:1110-1119
       } else {
         reach = (d_goal < thr_goal) && (c.flags & GMPE_FLAG_USE_DONES) && !st_pre;
@@ -305,7 +310,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         const bool close = d < sep;
         ncoll_rew += (close && !st_k && !st_pre);    // is_collision at reward(i) time (july:907-914)
         ncoll_info += (close && !st_k && !st_post);  // ... at info_callback(i) time (july:785)
-        if (tp && st_k) nbr_excl |= 1u << k;
+        if (tp && !sc && st_k) nbr_excl |= 1u << k;  // sc:1470-1476 keeps done agents as neighbours
         if (tube) {  // front / back neighbours along the own heading (july:1136-1143, tp:991-1003)
           const Real rx = PX[k] - s.x, ry = PY[k] - s.y;
           const Real proj = rx * hx + ry * hy;
@@ -349,14 +354,15 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         rew = clip(rew, -Real(4) * coll, goal * Real(5));
         rew = clip(rew, Real(c.min_reward), Real(c.max_reward));
       } else if (tp) {  // Scenario.reward (tp:957-1159, tp2:955-1140)
-        if (!tp2) rew -= Real(ncoll_rew) * coll;  // commented out in tp2:962-970
+        if (!tp2) rew -= Real(ncoll_rew) * coll * Real(sc ? 4 : 1);  // commented out in tp2:962-970; x4 in sc:1131-1137
         Real ts, ty;
         tp_tube_coords<Real>(wf, s.x, s.y, ts, ty);
         const Real L = wf[GMPE_WF_L], hw = wf[GMPE_WF_HALF_W];
-        const bool valid_exit = tp_in_exit_gate(ts, ty, L, hw);
+        const bool valid_exit = tp_in_exit_gate(ts, ty, L, hw, Real(sc ? 0.05 : 0.02));
         if (ph == 2 && ph > pp + 1) rew -= goal;  // tp:1018-1019
         if (ph == pp + 1 && pr == ph - 1) {       // tp:1028-1042
-          if (ph == 1 && tp_in_entrance_gate(ts, ty, L, hw) && cool == 0) { rew += goal; cool = c.episode_length; pr = 1; }
+          // cooldown: episode_length steps (tp:255); episode_length / 10 truncated by the int32 array in sc:268
+          if (ph == 1 && tp_in_entrance_gate(ts, ty, L, hw) && cool == 0) { rew += goal; cool = sc ? (int)((double)c.episode_length / 10) : c.episode_length; pr = 1; }
           else if (ph == 2) { rew += goal; pr = 2; if (tp2 && reach) rew += goal * Real(5); }
         }
         // |heading error| to the corridor axis: sin / cos of (theta - corridor_heading) from the unit vectors
@@ -365,7 +371,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         if (ph == 0) {  // tp:1044-1063
           const Real d = tp_entrance_gate_distance(ts, ty, hw);
           rew -= d;
-          if (d < Real(c.world_size * 0.1)) rew -= he * Real(c.formation_rew) * Real(0.5);
+          if (!sc && d < Real(c.world_size * 0.1)) rew -= he * Real(c.formation_rew) * Real(0.5);
         } else if (ph == 1) {  // tp:1065-1108
           if (front >= 0) { const Real diff = fdist - sep; sp_err += diff < Real(0) ? abs_(diff) : Real(0); }
           if (back >= 0) { const Real diff = bdist - sep; sp_err += diff < Real(0) ? abs_(diff) : Real(0); }
@@ -373,17 +379,27 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
           rew -= sp_err * Real(c.formation_rew);
           rew -= tp_exit_gate_distance(ts, ty, L, hw);
           cnt[GMPE_AC_STEPS_IN_CORRIDOR] += 1;
-          rew -= he * Real(c.formation_rew) * Real(0.1);
+          if (!sc) rew -= he * Real(c.formation_rew) * Real(0.1);
+          else {  // sc:1265-1276: progress along the tube axis since the last in-tube step
+            const Real tdx = wf[GMPE_WF_EXIT_X] - wf[GMPE_WF_ENT_X], tdy = wf[GMPE_WF_EXIT_Y] - wf[GMPE_WF_ENT_Y];
+            const Real tl = norm2(tdx, tdy);
+            const Real proj = (s.x - wf[GMPE_WF_ENT_X]) * div_(tdx, tl) + (s.y - wf[GMPE_WF_ENT_Y]) * div_(tdy, tl);
+            const Real dp = proj - Real(prev_proj);
+            rew += Real(c.goal_rew / (c.world_size * 0.8 * 10)) * (dp > Real(-0.05) ? dp : Real(-0.05));  // progress_gain sc:538
+            prev_proj = (float)proj;
+          }
+        } else if (sc && pr == 0) {  // sc:1278-1279
+          cur = 0;
         } else if (!tp2) {  // tp:1110-1123 (tp2 has no post-tube term)
           if (d_goal < thr_goal) { if (reach) rew += goal * Real(5); }
           else rew -= d_goal;
         }
-        if (pr == 1 && ph == 0) cnt[GMPE_AC_CONFORMANCE] += 1;
-        if (ph > pr) pr = ph;
-        if (ph < pp) rew -= coll;
-        if (ph < pr) rew -= coll;
-        pp = ph;
-        if (tp_in_tube_rect(ts, ty, L, hw) && ph != 1 && (tp2 || !valid_exit)) rew -= coll;  // tp:1145-1147, tp2:1130-1132
+        if (pr == 1 && cur == 0) cnt[GMPE_AC_CONFORMANCE] += 1;
+        if (cur > pr) pr = cur;
+        if (cur < pp) rew -= coll;
+        if (cur < pr) rew -= coll;
+        pp = cur;
+        if (tp_in_tube_rect(ts, ty, L, hw) && cur != 1 && (tp2 || sc || !valid_exit)) rew -= coll;  // tp:1145-1147, tp2:1130-1132, sc:1308-1310
         if (ts > L && pr < 1) rew -= goal;                                           // tp:1149-1151
         rew = clip(rew, -Real(4) * coll, goal * Real(5));
       } else {
@@ -472,6 +488,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         if (i == 0) g_wi[(size_t)b * GMPE_WORLD_I + GMPE_WI_STEP] = wstep;
         if (tube && do_info && i == N - 1) g_wf[(size_t)b * GMPE_WORLD_F + GMPE_WF_DELTA_SPACING] = dsum;
         if (tp) p.st.agent_ext[ga * 2] = cool;
+        if (sc) p.st.agent_ext[ga * 2 + 1] = __float_as_int(prev_proj);
         if (do_info) {
           int4* gc = (int4*)(g_cnt + ga * GMPE_AGENT_CNT);
           gc[0] = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
@@ -540,7 +557,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       if (tp) {  // phase_reached and the cooldown were cleared by reset_world (tp:346-348)
         Real ts, ty;
         tp_tube_coords<Real>(wf, s.x, s.y, ts, ty);
-        ph_obs = tp_phase<Real, tp2>(ts, ty, wf[GMPE_WF_L], wf[GMPE_WF_HALF_W], pp, 0);
+        ph_obs = tp_phase<Real, TPV>(ts, ty, wf[GMPE_WF_L], wf[GMPE_WF_HALF_W], pp, 0);
         p.st.agent_ext[ga * 2] = 0;
         p.st.agent_ext[ga * 2 + 1] = 0;
       }
@@ -628,7 +645,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     for (int k = 0; k < N; ++k) {
       const bool dead = st_post || STF[k];
       // tp never records goal_tracker (tp:1119 is commented out): landmarks stay connected there
-      const bool lm_i_dead = tp ? false : (bool)st_post, lm_k_dead = tp ? false : (bool)STF[k];
+      const bool lm_i_dead = (tp && !sc) ? false : (bool)st_post, lm_k_dead = (tp && !sc) ? false : (bool)STF[k];  // sc:1294 records goal_tracker
       // agent i -> agent k, agent i -> landmark k
       row_a[k] = (k == i || dead) ? Real(0) : daa[k];
       row_a[N + k] = (st_post || lm_k_dead) ? Real(0) : dal[k];
@@ -691,8 +708,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         Real cn = ex_ * hx + ey_ * hy, sn_ = ex_ * hy - ey_ * hx;  // cos / sin of (theta - corridor_heading)
         const Real nrm = norm2(cn, sn_);                             // e is a unit vector up to 1e-9
         cn = div_(cn, nrm); sn_ = div_(sn_, nrm);
-        o[12] = trunc32(cn); o[13] = trunc32(sn_);
-        o[14] = Real(ph_obs);
+        if (sc) o[12] = Real(ph_obs);  // sc:1536-1548: no heading-alignment pair
+        else { o[12] = trunc32(cn); o[13] = trunc32(sn_); o[14] = Real(ph_obs); }
       } else if (obs_direct) {
         if (wr && g_obs) {
           V2* o = reinterpret_cast<V2*>((Real*)p.out.obs + ga * F);

@@ -286,8 +286,8 @@ __device__ __forceinline__ bool tp_in_entrance_gate(Real s, Real y, Real L, Real
   return (-(Real(0.02) * L) - Real(0.05) <= s) && (s <= Real(0.08) * L + Real(0.05)) && (abs_(y) <= hw + Real(0.05));
 }
 template <typename Real>
-__device__ __forceinline__ bool tp_in_exit_gate(Real s, Real y, Real L, Real hw) {  // tp:618-621, 586-587
-  return (L - Real(0.02) * L - Real(0.05) <= s) && (s <= L + Real(0.08) * L + Real(0.05)) && (abs_(y) <= hw + Real(0.05));
+__device__ __forceinline__ bool tp_in_exit_gate(Real s, Real y, Real L, Real hw, Real back = Real(0.02)) {  // tp:618-621, 586-587
+  return (L - back * L - Real(0.05) <= s) && (s <= L + Real(0.08) * L + Real(0.05)) && (abs_(y) <= hw + Real(0.05));
 }
 template <typename Real>
 __device__ __forceinline__ Real tp_entrance_gate_distance(Real s, Real y, Real hw) {  // tp:610-615
@@ -302,13 +302,17 @@ __device__ __forceinline__ Real tp_exit_gate_distance(Real s, Real y, Real L, Re
 // two_phase_graph.py ("tp2", TWO = true) lacks the "previous_phase == 2 and valid_exit" branch
 // (tp:681-683 vs tp2:676-681); where tp2 falls off the end and returns None (an agent beyond the
 // exit plane that never entered: float(None) raises in the reference) this build returns 0.
-template <typename Real, bool TWO>
+// VARIANT: 0 three_phase_graph.py, 1 two_phase_graph.py, 2 nav_graph_metered_single_corridor_rot_inv.py
+// ("sc": inside the tube the phase stays 1, sc:693-695; exit gate reaches 0.05 L back, sc:621).
+template <typename Real, int VARIANT>
 __device__ __forceinline__ int tp_phase(Real s, Real y, Real L, Real hw, int pp, int pr) {
+  constexpr bool TWO = VARIANT == 1, SC = VARIANT == 2;
   const bool in_tube = tp_in_tube_rect(s, y, L, hw), passed = s > L;
-  const bool valid_exit = tp_in_exit_gate(s, y, L, hw);
+  const bool valid_exit = tp_in_exit_gate(s, y, L, hw, Real(SC ? 0.05 : 0.02));
   if (!in_tube && !passed) return 0;
   if (in_tube) {
     if (pp == 0) return tp_in_entrance_gate(s, y, L, hw) ? 1 : 0;
+    if (SC) return 1;
     if (TWO) return (pp == 1 && valid_exit) ? 2 : 1;
     return valid_exit ? 2 : 1;  // pp is 1 or 2 here
   }

@@ -244,7 +244,7 @@ def load(name: str):
     from . import config
 
     base = name[:-3] if name.endswith(".py") else name
-    if base not in config.JULY_SCENARIOS + config.NAV_SCENARIOS + config.THREE_PHASE_SCENARIOS + config.TWO_PHASE_SCENARIOS:
+    if base not in config.JULY_SCENARIOS + config.NAV_SCENARIOS + config.THREE_PHASE_SCENARIOS + config.TWO_PHASE_SCENARIOS + config.CORRIDOR_ROT_INV_SCENARIOS:
         raise FileNotFoundError(f"no scenario {name!r} in this build")
     import sys
     return sys.modules[__name__]

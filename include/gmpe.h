@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GMPE_ABI_VERSION 8
+#define GMPE_ABI_VERSION 9
 
 /* error codes */
 #define GMPE_OK 0
@@ -45,6 +45,9 @@ extern "C" {
 #define GMPE_SCEN_TWO_PHASE 3 /* two_phase_graph.py (eval_scripts/commands_test_run.txt:14): the same family;
                                  the goal is the tube exit -- an agent is done when it leaves through the
                                  exit gate; no agent-collision penalty; same layouts and restrictions */
+#define GMPE_SCEN_CORRIDOR_ROT_INV 4 /* nav_graph_metered_single_corridor_rot_inv.py (the scenario of
+                                 model_weights/tube/rot_inv/airtaxi): 13-d obs, progress reward along the
+                                 tube (prev_proj), fixed tube length; same restrictions */
 /* GmpeConfig.dynamics -- multiagent/core.py:23-26 EntityDynamicsType */
 #define GMPE_DYN_DOUBLE_INTEGRATOR 0
 #define GMPE_DYN_UNICYCLE 1
@@ -169,8 +172,8 @@ typedef struct GmpeConfig {
 typedef struct GmpeLayout {
   int32_t real_bytes;   /* 4 or 8 */
   int32_t num_entities; /* E = N+L+O+W */
-  int32_t obs_dim;      /* F_obs: 19 july, 6 nav, 15 two/three_phase */
-  int32_t node_dim;     /* F_node: 8 (7 two/three_phase) */
+  int32_t obs_dim;      /* F_obs: 19 july, 6 nav, 15 two/three_phase, 13 corridor_rot_inv */
+  int32_t node_dim;     /* F_node: 8 (7 for the rot-inv family) */
   int32_t edge_cap;     /* E*(E-1) */
   int32_t info_dim;     /* GMPE_INFO_K */
   int64_t agent_state, agent_aux, agent_flags, agent_cnt;
@@ -191,8 +194,9 @@ typedef struct GmpeState {
   void* landmarks;      /* Real [B][L][2]                                                              */
   void* obstacles;      /* Real [B][O][2]  (may be NULL when O == 0)                                   */
   void* walls;          /* Real [B][W][GMPE_WALL_F] (may be NULL when W == 0)                          */
-  int32_t* agent_ext;   /* i32  [B][N][2]: entry_reward_cooldown (three_phase_graph.py:348,652-654,1037),
-                           spare.  GMPE_SCEN_THREE_PHASE / TWO_PHASE only; may be NULL for the other scenarios      */
+  int32_t* agent_ext;   /* i32  [B][N][2]: entry_reward_cooldown (three_phase_graph.py:348,652-654,1037);
+                           the bits of the float32 prev_proj (nav_graph_metered_single_corridor_rot_inv.py:
+                           374,1268-1276).  Rot-inv family only; may be NULL for the other scenarios           */
 } GmpeState;
 
 /* Per-step outputs (device pointers, caller-owned).  Any pointer may be NULL to

@@ -681,6 +681,8 @@ static void july_info(World* w, int i, double* info) {
  * july (diff of tp:315-399, 723-815, 847-956 against july:339-420, 741-829, 864-973 is empty up
  * to a float32 cast and one extra info key), so those are shared. */
 static int is_two_phase(const World* w) { return w->c->scenario == GMPE_SCEN_TWO_PHASE; } /* two_phase_graph.py ("tp2") */
+/* nav_graph_metered_single_corridor_rot_inv.py ("sc"): same family again */
+static int is_corridor(const World* w) { return w->c->scenario == GMPE_SCEN_CORRIDOR_ROT_INV; }
 static double agent_theta(const World* w, int i) { /* state.theta; arctan2(vy, vx) for the DI (core:188-189) */
   const double* s = w->as + i * 4;
   return is_kin_heading(w->c) ? s[2] : atan2(s[3], s[2]);
@@ -710,10 +712,11 @@ static int tp_in_entrance_gate(double s, double y, double L, double hw) { /* tp:
   double gf = 0.08 * L, gb = 0.02 * L;
   return (-gb - 0.05 <= s && s <= gf + 0.05) && (fabs(y) <= hw + 0.05);
 }
-static int tp_in_exit_gate(double s, double y, double L, double hw) { /* tp:618-621, ratios tp:586-587 */
-  double eb = 0.02 * L, ef = 0.08 * L;
+static int tp_in_exit_gate_r(double s, double y, double L, double hw, double back_ratio) { /* tp:618-621, ratios tp:586-587 (sc:621: 0.05) */
+  double eb = back_ratio * L, ef = 0.08 * L;
   return (L - eb - 0.05 <= s && s <= L + ef + 0.05) && (fabs(y) <= hw + 0.05);
 }
+#define tp_in_exit_gate(s, y, L, hw) tp_in_exit_gate_r(s, y, L, hw, is_corridor(w) ? 0.05 : 0.02)
 
 /* get_agent_phase tp:639-705: decrements the entry cooldown on EVERY call (observation and
  * reward both call it); does not touch previous_phase */
@@ -729,6 +732,7 @@ static int tp_get_agent_phase(World* w, int i) {
   if (!in_tube && !passed) return 0;
   if (in_tube) {
     if (pp == 0) return valid_entrance ? 1 : 0;
+    if (is_corridor(w)) return 1; /* sc:693-695 */
     if (pp == 1 && valid_exit) return 2;
     if (pp == 2 && valid_exit && !is_two_phase(w)) return 2; /* tp:681-683; absent from tp2:676-681 */
     return 1;
@@ -755,7 +759,7 @@ static void tp_observation(World* w, int i, double* o) {
   double nd[MAXN], nr[MAXN][2];
   int order[MAXN], m = 0;
   for (int k = 0; k < w->N; ++k) { /* tp:1182-1191: done agents are not neighbours */
-    if (k == i || w->fl[k * 4 + GMPE_AF_STATUS]) continue;
+    if (k == i || (w->fl[k * 4 + GMPE_AF_STATUS] && !is_corridor(w))) continue; /* sc:1470-1476 keeps done agents */
     nr[m][0] = w->as[k * 4] - p[0]; nr[m][1] = w->as[k * 4 + 1] - p[1];
     nd[m] = norm2(nr[m][0], nr[m][1]);
     order[m] = m; ++m;
@@ -778,6 +782,11 @@ static void tp_observation(World* w, int i, double* o) {
   double raw[15] = {cos(h), sin(h), speed, g[0], g[1], nn[0], nn[1], nn[2], nn[3],
                     clipd(s / L, -2.0, 2.0), clipd(y / (hw + 1e-9), -2.0, 2.0),
                     tp_exit_gate_distance(s, y, L, hw) / (L + 1e-9), cos(he), sin(he), (double)phase};
+  if (is_corridor(w)) { /* sc:1536-1548: no heading-alignment pair -> 13 values */
+    raw[12] = raw[14];
+    for (int q = 0; q < 13; ++q) o[q] = (double)(float)raw[q];
+    return;
+  }
   for (int q = 0; q < 15; ++q) o[q] = (double)(float)raw[q]; /* .astype(np.float32), tp:1250 */
 }
 
@@ -789,9 +798,9 @@ static double tp_reward(World* w, int i, double theta_draw) {
   double* st = w->as + i * 4;
   uint8_t* fl = w->fl + i * 4;
   int32_t* cnt = w->cnt + i * GMPE_AGENT_CNT;
-  for (int a = 0; a < w->N && !is_two_phase(w); ++a) { /* tp:965-970; commented out in tp2:962-970 */
+  for (int a = 0; a < w->N && !is_two_phase(w); ++a) { /* tp:965-970; commented out in tp2:962-970; x4 in sc:1131-1137 */
     if (a == i) continue;
-    if (is_collision(w, a, i)) rew -= c->collision_rew;
+    if (is_collision(w, a, i)) rew -= c->collision_rew * (is_corridor(w) ? 4 : 1);
   }
   double theta = agent_theta(w, i);
   double hx = cos(theta), hy = sin(theta);
@@ -811,7 +820,9 @@ static double tp_reward(World* w, int i, double theta_draw) {
   if (phase == pp + 1 && fl[GMPE_AF_PHASE_REACHED] == phase - 1) { /* tp:1028-1042 */
     if (phase == 1 && tp_in_entrance_gate(s, y, L, hw) && w->ext[i * 2] == 0) {
       rew += c->goal_rew;
-      w->ext[i * 2] = c->episode_length; /* phase_reward_cooldown_steps = episode_length (tp:255) */
+      /* phase_reward_cooldown_steps = episode_length (tp:255), episode_length / 10 in sc:268 (a float,
+       * truncated by the int32 array it is stored in) */
+      w->ext[i * 2] = is_corridor(w) ? (int32_t)((double)c->episode_length / 10) : c->episode_length;
       fl[GMPE_AF_PHASE_REACHED] = 1;
     } else if (phase == 2) {
       rew += c->goal_rew;
@@ -829,7 +840,7 @@ static double tp_reward(World* w, int i, double theta_draw) {
     double d = tp_entrance_gate_distance(s, y, hw);
     rew -= d;
     double he = fabs(pymod2pi(theta - corridor_heading + PI_D) - PI_D);
-    if (d < c->world_size * 0.1) rew -= he * c->formation_rew * 0.5;
+    if (d < c->world_size * 0.1 && !is_corridor(w)) rew -= he * c->formation_rew * 0.5; /* no heading term in sc:1246-1249 */
   } else if (phase == 1) { /* tp:1065-1108 */
     double spacing_error = 0;
     if (front >= 0) {
@@ -846,7 +857,21 @@ static double tp_reward(World* w, int i, double theta_draw) {
     cnt[GMPE_AC_STEPS_IN_CORRIDOR] += 1;
     if (!is_two_phase(w)) w->wf[GMPE_WF_DELTA_SPACING] += spacing_error; /* tp:1101; not in tp2 */
     double he = fabs(pymod2pi(theta - corridor_heading + PI_D) - PI_D);
-    rew -= he * c->formation_rew * 0.1;
+    if (!is_corridor(w)) rew -= he * c->formation_rew * 0.1;
+    else { /* sc:1265-1276: progress along the tube axis since the last in-tube step (prev_proj is float32) */
+      double tdx = w->wf[GMPE_WF_EXIT_X] - w->wf[GMPE_WF_ENT_X], tdy = w->wf[GMPE_WF_EXIT_Y] - w->wf[GMPE_WF_ENT_Y];
+      double tl = norm2(tdx, tdy);
+      double proj = (st[0] - w->wf[GMPE_WF_ENT_X]) * (tdx / tl) + (st[1] - w->wf[GMPE_WF_ENT_Y]) * (tdy / tl);
+      float prev;
+      memcpy(&prev, &w->ext[i * 2 + 1], 4);
+      double dp = proj - (double)prev;
+      double gain = c->goal_rew / (c->world_size * 0.8 * 10); /* progress_gain, sc:538 */
+      rew += gain * (dp > -0.05 ? dp : -0.05);
+      float pf = (float)proj;
+      memcpy(&w->ext[i * 2 + 1], &pf, 4);
+    }
+  } else if (phase == 2 && is_corridor(w) && fl[GMPE_AF_PHASE_REACHED] == 0) {
+    phase = 0; /* sc:1278-1279 */
   } else if (phase == 2 && !is_two_phase(w)) { /* tp:1110-1123; goal_tracker is NOT updated here (line commented out) */
     double d = norm2(st[0] - w->lm[i * 2], st[1] - w->lm[i * 2 + 1]);
     if (d < c->goal_dist_thresh) {
@@ -854,7 +879,7 @@ static double tp_reward(World* w, int i, double theta_draw) {
         fl[GMPE_AF_STATUS] = 1;
         if (is_kin_heading(c)) { st[2] = theta_draw; st[3] = c->v_min; }
         else { st[2] = 0; st[3] = 0; }
-        rew += c->goal_rew * 5;
+        rew += c->goal_rew * 5; /* sc:1294 also records goal_tracker: see tp_mask_adj */
       }
     } else rew -= d;
   }
@@ -863,7 +888,7 @@ static double tp_reward(World* w, int i, double theta_draw) {
   if (phase < fl[GMPE_AF_PREV_PHASE]) rew -= c->collision_rew;
   if (phase < fl[GMPE_AF_PHASE_REACHED]) rew -= c->collision_rew;
   fl[GMPE_AF_PREV_PHASE] = (uint8_t)phase;
-  if (tp_in_tube_rect(s, y, L, hw) && phase != 1 && (is_two_phase(w) || !valid_exit)) rew -= c->collision_rew; /* tp:1145-1147, tp2:1130-1132 */
+  if (tp_in_tube_rect(s, y, L, hw) && phase != 1 && (is_two_phase(w) || is_corridor(w) || !valid_exit)) rew -= c->collision_rew; /* tp:1145-1147, tp2:1130-1132, sc:1308-1310 */
   if (s > L && fl[GMPE_AF_PHASE_REACHED] < 1) rew -= c->goal_rew;                             /* tp:1149-1151 */
   return clipd(rew, -4 * c->collision_rew, c->goal_rew * 5);
 }
@@ -902,6 +927,7 @@ static void tp_node_features(World* w, int ego, double* out /* [E][7] */) {
 /* graph_observation mask tp:1331-1343: goal_tracker is never set in this scenario, so only
  * done agents are disconnected */
 static void tp_mask_adj(World* w) {
+  if (is_corridor(w)) { mask_adj(w); return; } /* sc:1294 records goal_tracker like july */
   for (int a = 0; a < w->N; ++a)
     if (w->fl[a * 4 + GMPE_AF_STATUS])
       for (int b = 0; b < w->E; ++b) { w->dist[a][b] = 0.0; w->dist[b][a] = 0.0; }
@@ -918,7 +944,7 @@ static void tp_random_scenario(World* w) {
   double width = fmax(3 * c->entity_size * 2.5, ws * 0.15);
   double angle = uni(seed, gw, ep, idx++, -PI_D / 2, PI_D / 2);
   double tl = ws * 0.8;
-  tl += uni(seed, gw, ep, idx++, -ws * 0.3, ws * 0.1); /* tp:503 */
+  if (!is_corridor(w)) tl += uni(seed, gw, ep, idx++, -ws * 0.3, ws * 0.1); /* tp:503; fixed length in sc:537 */
   double ca = cos(angle), sa = sin(angle);
   double ent[2] = {sa * (tl / 4), ca * (tl / 4)};
   double ext[2] = {sa * (-tl / 4), ca * (-tl / 4)};
@@ -1137,13 +1163,17 @@ static void write_graph_outputs(World* w, const GmpeStepOut* out) {
 }
 
 /* MultiAgentGraphEnv.reset env:1066-1081 -> reset_world july:339-420 */
-static int rot_inv(const GmpeConfig* c) { return c->scenario == GMPE_SCEN_THREE_PHASE || c->scenario == GMPE_SCEN_TWO_PHASE; }
-static int obs_dim_of(const GmpeConfig* c) { return c->scenario == GMPE_SCEN_JULY_TUBE ? 19 : (rot_inv(c) ? 15 : 6); }
+static int rot_inv(const GmpeConfig* c) {
+  return c->scenario == GMPE_SCEN_THREE_PHASE || c->scenario == GMPE_SCEN_TWO_PHASE || c->scenario == GMPE_SCEN_CORRIDOR_ROT_INV;
+}
+static int obs_dim_of(const GmpeConfig* c) {
+  return c->scenario == GMPE_SCEN_JULY_TUBE ? 19 : (c->scenario == GMPE_SCEN_CORRIDOR_ROT_INV ? 13 : (rot_inv(c) ? 15 : 6));
+}
 static int node_dim_of(const GmpeConfig* c) { return rot_inv(c) ? 7 : 8; }
 static void scen_observation(World* w, int i, double* o) {
   switch (w->c->scenario) {
     case GMPE_SCEN_JULY_TUBE: july_observation(w, i, o); break;
-    case GMPE_SCEN_THREE_PHASE: case GMPE_SCEN_TWO_PHASE: tp_observation(w, i, o); break;
+    case GMPE_SCEN_THREE_PHASE: case GMPE_SCEN_TWO_PHASE: case GMPE_SCEN_CORRIDOR_ROT_INV: tp_observation(w, i, o); break;
     default: nav_observation(w, i, o);
   }
 }

@@ -169,7 +169,7 @@ def run_july_trace(path, seed, T, policy, eps=0.15, episodes=1, **over):
     rec = {k: [] for k in (
         "actions theta_draw state p_dist status prev_phase phase_reached goal_reached obs node_obs adj "
         "reward done info cnt delta_spacing_sum edge_index edge_attr num_edges "
-        "gnn_edge_index gnn_edge_attr gnn_num_edges cooldown").split()}
+        "gnn_edge_index gnn_edge_attr gnn_num_edges cooldown prev_proj").split()}
     inits = {k: [] for k in "agent_state prev_phase tube landmarks obstacles goal_min_time reset_obs reset_node_obs reset_adj".split()}
 
     for ep in range(episodes):
@@ -218,6 +218,7 @@ def run_july_trace(path, seed, T, policy, eps=0.15, episodes=1, **over):
             rec["delta_spacing_sum"].append(float(np.sum(sc.delta_spacing)))
             # three_phase family: entry_reward_cooldown (three_phase_graph.py:348, 652-654, 1037)
             rec["cooldown"].append(np.array(getattr(sc, "entry_reward_cooldown", np.zeros(n)), dtype=np.int64).copy())
+            rec["prev_proj"].append(np.array(getattr(sc, "prev_proj", np.zeros(n)), dtype=np.float32).copy())
             rec["edge_index"].append(ei); rec["edge_attr"].append(ea); rec["num_edges"].append(ne)
             rec["gnn_edge_index"].append(gei); rec["gnn_edge_attr"].append(gea); rec["gnn_num_edges"].append(gne)
 
@@ -322,6 +323,11 @@ def main():
     run_july_trace(g("two_phase_n3_pursuit_s31.npz"), seed=31, T=150, policy="pursuit", scenario_name="two_phase_graph")
     run_july_trace(g("two_phase_n3_pursuit_s32_ep2.npz"), seed=32, T=110, policy="pursuit", eps=0.3, episodes=2,
                    scenario_name="two_phase_graph")
+    # ... and nav_graph_metered_single_corridor_rot_inv.py (model_weights/tube/rot_inv/airtaxi)
+    run_july_trace(g("corridor_rot_inv_n3_pursuit_s41.npz"), seed=41, T=150, policy="pursuit",
+                   scenario_name="nav_graph_metered_single_corridor_rot_inv")
+    run_july_trace(g("corridor_rot_inv_n3_pursuit_s42_ep2.npz"), seed=42, T=110, policy="pursuit", eps=0.3, episodes=2,
+                   scenario_name="nav_graph_metered_single_corridor_rot_inv")
     # stage-1 force physics: the live classic-MPE World.step
     run_classic_trace(g("classic_spread_n3_s11.npz"), seed=11, T=120)
     run_classic_trace(g("classic_spread_n6_s12.npz"), seed=12, T=80, num_agents=6, num_landmarks=6)

@@ -11,7 +11,7 @@ from golden_util import Trace, traces
 from gmpe_b200 import abi
 
 pytestmark = pytest.mark.gpu
-ALL = traces("july_*.npz") + traces("three_phase_*.npz") + traces("two_phase_*.npz")
+ALL = traces("july_*.npz") + traces("three_phase_*.npz") + traces("two_phase_*.npz") + traces("corridor_rot_inv_*.npz")
 
 
 def _close(a, b, atol, rtol, what):
@@ -61,8 +61,11 @@ def run_trace(tr: Trace, precision: str, teacher_force: bool, atol: float, rtol:
             assert (fl[:, abi.AF_PHASE_REACHED] == z["phase_reached"][t]).all(), tag + " phase_reached"
             assert (fl[:, abi.AF_GOAL_REACHED].astype(int) - 1 == z["goal_reached"][t]).all(), tag + " goal_reached"
             assert (out["obs"][0][:, -1].cpu().numpy() == z["obs"][t][:, -1]).all(), tag + " phase"
-            if tr.name.startswith(("three_phase", "two_phase")):
+            if tr.name.startswith(("three_phase", "two_phase", "corridor_rot_inv")):
                 assert (eng.state["agent_ext"][0, :, 0].cpu().numpy() == z["cooldown"][t]).all(), tag + " cooldown"
+                if tr.name.startswith("corridor_rot_inv"):  # prev_proj: float32 bits in the second slot
+                    pj = eng.state["agent_ext"][0, :, 1].cpu().numpy().view(np.float32)
+                    assert np.abs(pj - z["prev_proj"][t]).max() <= max(atol, 1e-6), tag + " prev_proj"
             assert (eng.state["agent_cnt"][0].cpu().numpy() == z["cnt"][t]).all(), tag + " counters"
             assert int(out["num_edges"][0]) == int(z["num_edges"][t]), tag + " num_edges"
             assert (out["edge_index"][0].cpu().numpy() == z["edge_index"][t]).all(), tag + " edge_index"
@@ -76,7 +79,7 @@ def run_trace(tr: Trace, precision: str, teacher_force: bool, atol: float, rtol:
 def test_fp64_free_running_bit_exact_graph(path):
     # three_phase emits float32 features (one float32 ulp of an O(1) value) and passes the
     # integrator's heading difference on to the reward through its heading-error terms
-    atol = 1e-6 if ("three_phase" in path or "two_phase" in path) else 2e-7
+    atol = 1e-6 if ("three_phase" in path or "two_phase" in path or "corridor_rot_inv" in path) else 2e-7
     run_trace(Trace(path), "fp64", teacher_force=False, atol=atol, rtol=0.0)
 
 

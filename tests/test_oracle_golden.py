@@ -7,7 +7,7 @@ from golden_util import Trace, traces
 from gmpe_b200 import abi
 from oracle.oracle import OracleEnv
 
-ALL = traces("july_*.npz") + traces("three_phase_*.npz") + traces("two_phase_*.npz")
+ALL = traces("july_*.npz") + traces("three_phase_*.npz") + traces("two_phase_*.npz") + traces("corridor_rot_inv_*.npz")
 
 
 def run_trace(tr: Trace, use_rk45: bool, teacher_force_state: bool):
@@ -46,8 +46,11 @@ def run_trace(tr: Trace, use_rk45: bool, teacher_force_state: bool):
             assert (fl[:, abi.AF_PHASE_REACHED] == z["phase_reached"][t]).all(), (tr.name, t, "phase_reached")
             assert (fl[:, abi.AF_GOAL_REACHED].astype(int) - 1 == z["goal_reached"][t]).all(), (tr.name, t, "goal_reached")
             assert (out["obs"][0][:, -1] == z["obs"][t][:, -1]).all(), (tr.name, t, "phase")
-            if "agent_ext" in env.state and tr.name.startswith(("three_phase", "two_phase")):
+            if "agent_ext" in env.state and tr.name.startswith(("three_phase", "two_phase", "corridor_rot_inv")):
                 assert (env.state["agent_ext"][0, :, 0] == z["cooldown"][t]).all(), (tr.name, t, "cooldown")
+                if tr.name.startswith("corridor_rot_inv"):  # prev_proj: float32 bits in the second slot
+                    pp = np.ascontiguousarray(env.state["agent_ext"][0, :, 1]).view(np.float32)
+                    assert np.abs(pp - z["prev_proj"][t]).max() <= 1e-6, (tr.name, t, "prev_proj")
             assert (env.state["agent_cnt"][0] == z["cnt"][t]).all(), (tr.name, t, "counters")
             assert out["num_edges"][0] == z["num_edges"][t], (tr.name, t, "num_edges")
             assert (out["edge_index"][0] == z["edge_index"][t]).all(), (tr.name, t, "edge_index")
@@ -63,7 +66,7 @@ def test_oracle_rk45_matches_reference_free_running(path):
     injected): the RK45 restatement tracks the reference to ~1e-12 over whole episodes
     and every discrete output is identical."""
     worst = run_trace(Trace(path), use_rk45=True, teacher_force_state=False)
-    f32_features = Trace(path).name.startswith(("three_phase", "two_phase"))  # that family emits float32 obs / node features
+    f32_features = Trace(path).name.startswith(("three_phase", "two_phase", "corridor_rot_inv"))  # that family emits float32 obs / node features
     for k, v in worst.items():
         tol = 1e-7 if k == "gnn_edge_attr" else 1e-10  # gnn attr is an fp32 value
         if f32_features and k in ("obs", "node_obs", "reset_obs", "reset_node"):
@@ -76,7 +79,7 @@ def test_oracle_closed_form_within_drift_bound(path):
     """The closed-form integrator (what the CUDA kernels use) against the reference's
     RK45: <= 1e-7 absolute free-running (SURVEY G10 / H3b measured 5.7e-8 over 200 steps)."""
     worst = run_trace(Trace(path), use_rk45=False, teacher_force_state=False)
-    f32_features = Trace(path).name.startswith(("three_phase", "two_phase"))
+    f32_features = Trace(path).name.startswith(("three_phase", "two_phase", "corridor_rot_inv"))
     for k, v in worst.items():
         # three_phase: its heading-error terms pass the integrator's 1e-8 heading difference on to the reward
         bound = 1e-6 if f32_features and k in ("obs", "node_obs", "reset_obs", "reset_node") else (5e-7 if f32_features else 2e-7)
