@@ -344,7 +344,8 @@ def run_ours(opts):
         v, done, ms = cpu_leg(wl["args"], sample_worlds, 50, 2, cores, max_seconds=15.0)
         cpu = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
                "sample": f"{done} steps x {sample_worlds} worlds of the same workload, {cores} pthreads, "
-                         "oracle/gmpe_oracle.c (fp64 C port of the reference step)"}
+                         "oracle/gmpe_oracle.c (fp64 C port of the reference step); the Python reference itself "
+                         "runs ~960 agent-steps/s per process (profiles/r1_python_reference_cpu.txt)"}
     line = {
         "metric": "agent-steps/sec (env step + graph obs)", "value": value, "unit": "agent-steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
