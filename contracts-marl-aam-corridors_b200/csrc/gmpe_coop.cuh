@@ -36,6 +36,12 @@ namespace gmpe {
 #endif
 // 1: adjacency rows (and even-width obs rows) leave the lane directly as 64/128-bit stores;
 // 0: staged in the slab and streamed out as contiguous 128-bit stores
+// 1: prefetch the next round's inputs into L2 at the top of a round.  Measured on B200: 31.3 ->
+// 29.9 us at 65,536 navigation worlds (2.2 rounds per warp) but 60.5 -> 63.9 us at 131,072 july
+// worlds (4.4 rounds), so it stays off by default.
+#ifndef GMPE_COOP_PREFETCH
+#define GMPE_COOP_PREFETCH 0
+#endif
 #ifndef GMPE_COOP_DIRECT_SMALL_ROWS
 #define GMPE_COOP_DIRECT_SMALL_ROWS 0
 #endif
@@ -87,6 +93,8 @@ __device__ __forceinline__ void copy_span(T* __restrict__ g, const unsigned char
       if ((world_mask >> (q / RW)) & 1u) g[q] = src[q];
   }
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <typename Real>
 __device__ __forceinline__ Real shfl_(Real v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -145,6 +153,26 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     const bool valid = lane_used && wl < nwv;
     const int64_t b = wbase + (valid ? wl : 0);                   // idle lanes shadow world wbase, never write
     const size_t ga = (size_t)b * N + (valid ? i : 0);            // global agent slot (lane-linear)
+
+    // The group this warp handles next: pull its inputs into L2 now, so that the loads at the
+    // top of the next round do not wait on DRAM (the step is short enough for that to show).
+    if (GMPE_COOP_PREFETCH) {
+      const int64_t grp_n = grp + (int64_t)gridDim.x * GMPE_COOP_WARPS;
+      if (grp_n < num_groups && lane_used) {
+        const int64_t bn = min(grp_n * WPW + wl, (int64_t)B - 1);
+        const size_t gn = (size_t)bn * N + i;
+        prefetch_l2((const V4*)g_as + gn);
+        prefetch_l2((const V2*)g_aux + gn);
+        prefetch_l2(g_fl + gn);
+        prefetch_l2((const V2*)g_lm + gn);
+        if (step_mode) prefetch_l2(p.act + gn);
+        if (do_info && step_mode) prefetch_l2(g_cnt + gn * GMPE_AGENT_CNT);
+        if (i == 0) {
+          if (tube) prefetch_l2(g_wf + (size_t)bn * GMPE_WORLD_F);
+          prefetch_l2(g_wi + (size_t)bn * GMPE_WORLD_I);
+        }
+      }
+    }
 
     // ---------------- loads: one agent per lane, coalesced ------------------------------
     V4 s = ((const V4*)g_as)[ga];
