@@ -533,12 +533,13 @@ __device__ __forceinline__ void masked_dist4(const typename RT<Real>::V2* pw, co
 
 // ---- the kernel ----------------------------------------------------------------------
 // Launch bounds picked by tools/sweep.py on a B200 (profiles/r1_sweep.txt): 128 threads with
-// >= 6 resident CTAs per SM (<= 85 registers) beat 256 x 1..4 on every workload measured.
+// >= 7 resident CTAs per SM (<= 72 registers) beat 256 x 1..4 and 128 x 3..6, 8 on the large-world
+// workloads (latency-bound: resident warps matter more than the extra spills).
 #ifndef GMPE_LB_THREADS
 #define GMPE_LB_THREADS 128
 #endif
 #ifndef GMPE_LB_MINBLOCKS
-#define GMPE_LB_MINBLOCKS 6
+#define GMPE_LB_MINBLOCKS 7
 #endif
 // NC / LC / OC / WC > 0: entity counts known at compile time (instantiated for the BASELINE
 // shapes 16/16/8/4 and 64/64/0/0 in fp32); NC == 0: every count is a launch-time value.
