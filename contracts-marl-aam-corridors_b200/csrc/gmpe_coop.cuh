@@ -45,6 +45,15 @@ namespace gmpe {
 #ifndef GMPE_COOP_DIRECT_SMALL_ROWS
 #define GMPE_COOP_DIRECT_SMALL_ROWS 0
 #endif
+// 1: the 16-byte aligned body of every staged span leaves shared memory as ONE bulk async copy
+// (cp.async.bulk.global.shared::cta, the TMA store path) issued by lane 0, and drains while the
+// warp loads and computes its next round; 0: the lanes stream it out with 128-bit stores.
+#ifndef GMPE_COOP_BULK_STORE
+#define GMPE_COOP_BULK_STORE 1
+#endif
+#ifndef GMPE_COOP_TRANSPOSE_TAIL
+#define GMPE_COOP_TRANSPOSE_TAIL 1
+#endif
 
 template <typename Real, int SCEN, int N>
 struct CoopTraits {
@@ -65,8 +74,23 @@ struct CoopTraits {
   static constexpr int NODE_BYTES = ND == 8 ? 0 : up16(AL * E * ND * R) + 16;
   static constexpr int ROUND_A = OBS_BYTES + ADJ_BYTES + NODE_BYTES;
   static constexpr int ROUND_B = EIDX_BYTES + EATTR_BYTES;
-  static constexpr int SLAB_BYTES = up16(ROUND_A > ROUND_B ? ROUND_A : ROUND_B);
+  // Bulk stores read the slab asynchronously: rounds A and B get separate regions when the
+  // resident CTAs still fit in shared memory, else they share one and B waits for A to drain.
+  static constexpr int MINBLOCKS = R == 4 ? GMPE_COOP_MINBLOCKS_F32 : GMPE_COOP_MINBLOCKS_F64;
+  static constexpr bool SPLIT = GMPE_COOP_BULK_STORE && (up16(ROUND_A + ROUND_B) + 0) * GMPE_COOP_WARPS * MINBLOCKS <= 200 * 1024;
+  static constexpr int B_OFF = SPLIT ? ROUND_A : 0;
+  static constexpr int SLAB_BYTES = SPLIT ? up16(ROUND_A + ROUND_B) : up16(ROUND_A > ROUND_B ? ROUND_A : ROUND_B);
 };
+
+// ---- bulk async store (shared::cta -> global), sm_90+ ------------------------------------
+__device__ __forceinline__ void bulk_store_issue(void* g, const void* s, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"((uint32_t)__cvta_generic_to_shared(s)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Contiguous span of n elements: shared -> global with 128-bit vectors.  The span was staged
 // at `slab + ((size_t)g & 15)` so that source and destination are co-aligned; a head / tail
@@ -82,10 +106,15 @@ __device__ __forceinline__ void copy_span(T* __restrict__ g, const unsigned char
     if (lane < head) g[lane] = src[lane];
     constexpr int VW = 16 / (int)sizeof(T);
     const int nv = (n - head) / VW;
-    const int4* s4 = reinterpret_cast<const int4*>(src + head);
-    int4* d4 = reinterpret_cast<int4*>(g + head);
+    if (GMPE_COOP_BULK_STORE) {
+      // every lane fenced its staging writes and the warp synchronised before this call
+      if (lane == 0 && nv > 0) bulk_store_issue(g + head, src + head, (uint32_t)nv * 16u);
+    } else {
+      const int4* s4 = reinterpret_cast<const int4*>(src + head);
+      int4* d4 = reinterpret_cast<int4*>(g + head);
 #pragma unroll 4
-    for (int q = lane; q < nv; q += 32) d4[q] = s4[q];
+      for (int q = lane; q < nv; q += 32) d4[q] = s4[q];
+    }
     for (int q = head + nv * VW + lane; q < n; q += 32) g[q] = src[q];
   } else {
 #pragma unroll 1
@@ -125,6 +154,12 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
 #endif
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* slab = smem_raw + (size_t)warp * T::SLAB_BYTES;
+  auto drain = [&]() {
+    if (GMPE_COOP_BULK_STORE) {
+      if (lane == 0) bulk_wait_read();
+      __syncwarp();
+    }
+  };
 
   Real* g_as = (Real*)p.st.agent_state;
   Real* g_aux = (Real*)p.st.agent_aux;
@@ -146,8 +181,18 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
   const bool lane_used = lane < AL;
   const int lb = lane_used ? wl * N : 0;  // first lane of this lane's world (shuffle base)
 
+  // Warp w of CTA c owns group r * (warps of the grid) + c * WARPS + w in round r.  The last,
+  // partial round is dealt out transposed (w * gridDim + c): its groups then spread over
+  // every CTA -- one warp each -- instead of filling the first CTAs, so that the SMs finish
+  // together at warp granularity.
   const int64_t num_groups = ((int64_t)B + WPW - 1) / WPW;
-  for (int64_t grp = (int64_t)blockIdx.x * GMPE_COOP_WARPS + warp; grp < num_groups; grp += (int64_t)gridDim.x * GMPE_COOP_WARPS) {
+  const int64_t grid_warps = (int64_t)gridDim.x * GMPE_COOP_WARPS;
+  const int64_t full_rounds = num_groups / grid_warps;
+  for (int64_t rnd = 0; rnd <= full_rounds; ++rnd) {
+    const int64_t slot = (GMPE_COOP_TRANSPOSE_TAIL && rnd == full_rounds) ? (int64_t)warp * gridDim.x + blockIdx.x
+                                                                            : (int64_t)blockIdx.x * GMPE_COOP_WARPS + warp;
+    const int64_t grp = rnd * grid_warps + slot;
+    if (grp >= num_groups) break;
     const int64_t wbase = grp * WPW;
     const int nwv = (int)min((int64_t)WPW, (int64_t)B - wbase);  // worlds of this warp
     const bool valid = lane_used && wl < nwv;
@@ -681,6 +726,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       row_l[k] = (lm_i_dead || STF[k]) ? Real(0) : norm2(lmi.x - PX[k], lmi.y - PY[k]);
       row_l[N + k] = (k == i || lm_i_dead || lm_k_dead) ? Real(0) : norm2(lmi.x - LX[k], lmi.y - LY[k]);
     }
+    drain();  // the previous round's bulk stores have finished reading the slab
     if (lane_used) {
       if (july) {  // Scenario.observation (july:1337-1463)
         Real d1 = Real(0), d2 = Real(0);
@@ -786,10 +832,12 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       for (int q = 0; q < N; ++q) { ra[q] = RT<Real>::mk2(row_a[2 * q], row_a[2 * q + 1]); rl[q] = RT<Real>::mk2(row_l[2 * q], row_l[2 * q + 1]); }
     }
     if (!obs_direct || !adj_direct || ND != 8) {
+      if (GMPE_COOP_BULK_STORE) fence_async_smem();
       __syncwarp();
       if (!obs_direct && g_obs) copy_span<Real, N * F>(g_obs, obs_region, nwv * N * F, all_worlds, wmask, lane);
       if (!adj_direct && g_adj) copy_span<Real, EE>(g_adj, adj_region, nwv * EE, all_worlds, wmask, lane);
       if (ND != 8 && g_nodew) copy_span<Real, N * E * ND>(g_nodew, node_region, nwv * N * E * ND, all_worlds, wmask, lane);
+      if (GMPE_COOP_BULK_STORE && lane == 0) bulk_commit();
       __syncwarp();
     }
 
@@ -805,8 +853,9 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       int32_t* g_ei = (pass == 0 ? p.out.edge_index : p.out.gnn_edge_index) + (size_t)wbase * 2 * CAP;
       Real* g_ea = (Real*)(pass == 0 ? p.out.edge_attr : p.out.gnn_edge_attr) + (size_t)wbase * CAP;
       int32_t* g_ne = pass == 0 ? p.out.num_edges : p.out.gnn_num_edges;
-      unsigned char* ei_region = slab;
-      unsigned char* ea_region = slab + T::EIDX_BYTES;
+      unsigned char* ei_region = slab + T::B_OFF;
+      unsigned char* ea_region = slab + T::B_OFF + T::EIDX_BYTES;
+      if (!T::SPLIT || pass == 1) drain();  // the region is still being read by an earlier bulk store
       int32_t* ei_w = reinterpret_cast<int32_t*>(ei_region + (reinterpret_cast<size_t>(g_ei) & 15));
       Real* ea_w = reinterpret_cast<Real*>(ea_region + (reinterpret_cast<size_t>(g_ea) & 15));
       uint32_t on_a = 0, on_l = 0;
@@ -843,13 +892,16 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
           if ((on_l >> q) & 1u) { ei[nl] = N + i; ei[CAP + nl] = q; ea[nl] = pass == 0 ? row_l[q] : Real((float)row_l[q]); ++nl; }
         }
       }
+      if (GMPE_COOP_BULK_STORE) fence_async_smem();
       __syncwarp();
       copy_span<int32_t, 2 * CAP>(g_ei, ei_region, nwv * 2 * CAP, all_worlds, wmask, lane);
       copy_span<Real, CAP>(g_ea, ea_region, nwv * CAP, all_worlds, wmask, lane);
+      if (GMPE_COOP_BULK_STORE && lane == 0) bulk_commit();
       if (wr && i == 0) g_ne[b] = n_edges;
       __syncwarp();
     }
   }
+  if (GMPE_COOP_BULK_STORE && lane == 0) bulk_wait_read();  // shared memory stays allocated until the copies have read it
 }
 
 }  // namespace gmpe
