@@ -51,6 +51,12 @@ namespace gmpe {
 #ifndef GMPE_COOP_BULK_STORE
 #define GMPE_COOP_BULK_STORE 1
 #endif
+// 1: the 8-wide node rows are staged like the 7-wide ones and leave as one span per warp
+// (whole 128-byte lines from the copy engine); 0: each lane stores its rows itself, one 32-byte
+// sector per line per instruction.
+#ifndef GMPE_COOP_STAGE_NODE
+#define GMPE_COOP_STAGE_NODE 0
+#endif
 #ifndef GMPE_COOP_TRANSPOSE_TAIL
 #define GMPE_COOP_TRANSPOSE_TAIL 1
 #endif
@@ -71,13 +77,14 @@ struct CoopTraits {
   static constexpr int EIDX_BYTES = up16(WPW * 2 * CAP * 4) + 16;
   static constexpr int EATTR_BYTES = up16(WPW * CAP * R) + 16;
   // 7-wide node rows (three_phase) are not whole sectors: the warp's rows are staged as one span
-  static constexpr int NODE_BYTES = ND == 8 ? 0 : up16(AL * E * ND * R) + 16;
+  static constexpr bool NODE_STAGED = ND != 8 || GMPE_COOP_STAGE_NODE;
+  static constexpr int NODE_BYTES = NODE_STAGED ? up16(AL * E * ND * R) + 16 : 0;
   static constexpr int ROUND_A = OBS_BYTES + ADJ_BYTES + NODE_BYTES;
   static constexpr int ROUND_B = EIDX_BYTES + EATTR_BYTES;
   // Bulk stores read the slab asynchronously: rounds A and B get separate regions when the
   // resident CTAs still fit in shared memory, else they share one and B waits for A to drain.
   static constexpr int MINBLOCKS = R == 4 ? GMPE_COOP_MINBLOCKS_F32 : GMPE_COOP_MINBLOCKS_F64;
-  static constexpr bool SPLIT = GMPE_COOP_BULK_STORE && (up16(ROUND_A + ROUND_B) + 0) * GMPE_COOP_WARPS * MINBLOCKS <= 200 * 1024;
+  static constexpr bool SPLIT = GMPE_COOP_BULK_STORE && (up16(ROUND_A + ROUND_B) + 0) * GMPE_COOP_WARPS * MINBLOCKS <= 220 * 1024;
   static constexpr int B_OFF = SPLIT ? ROUND_A : 0;
   static constexpr int SLAB_BYTES = SPLIT ? up16(ROUND_A + ROUND_B) : up16(ROUND_A > ROUND_B ? ROUND_A : ROUND_B);
 };
@@ -680,21 +687,33 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     // ---------------- emission: node features of ego = this lane's agent ---------------------
     // _get_entity_feat_relative (july:1694-1771): [rel_vel, rel_pos, rel_goal, occupied, type];
     // ego i sees agents <= i with their post-reward velocity, agents > i pre-reward
-    if (ND == 8 && p.out.node_obs && wr) {
-      Real* g_node = (Real*)p.out.node_obs + ga * (size_t)(E * 8);
+    if (T::NODE_STAGED) drain();  // the previous round's bulk stores have finished reading the slab
+    if (ND == 8 && p.out.node_obs && (T::NODE_STAGED ? lane_used : wr)) {
+      // staged rows sit 16-byte aligned in the slab (node_obs itself is 32-byte aligned: gmpe.h)
+      Real* g_node = T::NODE_STAGED ? reinterpret_cast<Real*>(slab + T::OBS_BYTES + T::ADJ_BYTES) + lane * (E * 8)
+                                    : (Real*)p.out.node_obs + ga * (size_t)(E * 8);
+      auto put_row = [&](Real* dst, const Real (&f)[8]) {
+        if (T::NODE_STAGED) {
+          V2* d2 = reinterpret_cast<V2*>(dst);
+          d2[0] = RT<Real>::mk2(f[0], f[1]); d2[1] = RT<Real>::mk2(f[2], f[3]);
+          d2[2] = RT<Real>::mk2(f[4], f[5]); d2[3] = RT<Real>::mk2(f[6], f[7]);
+        } else {
+          store_row8(dst, f);
+        }
+      };
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         const bool post = k <= i;
         const Real vkx = post ? VQX[k] : VPX[k], vky = post ? VQY[k] : VPY[k];
         const Real f[8] = {vkx - vpost.x, vky - vpost.y, PX[k] - s.x, PY[k] - s.y,
                            LX[k] - s.x, LY[k] - s.y, Real(0), Real(0)};  // landmark_poses[entity.id] (july:1740)
-        store_row8(g_node + k * 8, f);
+        put_row(g_node + k * 8, f);
       }
 #pragma unroll
       for (int l = 0; l < N; ++l) {
         const Real rx = LX[l] - s.x, ry = LY[l] - s.y;
         const Real f[8] = {Real(0) - vpost.x, Real(0) - vpost.y, rx, ry, rx, ry, Real(1), Real(1)};
-        store_row8(g_node + (N + l) * 8, f);
+        put_row(g_node + (N + l) * 8, f);
       }
     }
 
@@ -708,7 +727,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     unsigned char* obs_region = slab;
     unsigned char* adj_region = slab + T::OBS_BYTES;
     unsigned char* node_region = slab + T::OBS_BYTES + T::ADJ_BYTES;  // 7-wide node rows only
-    Real* g_nodew = (ND != 8 && p.out.node_obs) ? (Real*)p.out.node_obs + (size_t)wbase * N * E * ND : nullptr;
+    Real* g_nodew = (T::NODE_STAGED && p.out.node_obs) ? (Real*)p.out.node_obs + (size_t)wbase * N * E * ND : nullptr;
     Real* adj_s = reinterpret_cast<Real*>(adj_region + (reinterpret_cast<size_t>(g_adj) & 15)) + wl * EE;
     Real* obs_s = reinterpret_cast<Real*>(obs_region + (reinterpret_cast<size_t>(g_obs) & 15)) + lane * F;
     // rows i and N + i of the masked distance matrix (july:1625-1648): done agents and the
@@ -726,7 +745,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       row_l[k] = (lm_i_dead || STF[k]) ? Real(0) : norm2(lmi.x - PX[k], lmi.y - PY[k]);
       row_l[N + k] = (k == i || lm_i_dead || lm_k_dead) ? Real(0) : norm2(lmi.x - LX[k], lmi.y - LY[k]);
     }
-    drain();  // the previous round's bulk stores have finished reading the slab
+    if (!T::NODE_STAGED) drain();  // the previous round's bulk stores have finished reading the slab
     if (lane_used) {
       if (july) {  // Scenario.observation (july:1337-1463)
         Real d1 = Real(0), d2 = Real(0);
@@ -831,12 +850,12 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
 #pragma unroll
       for (int q = 0; q < N; ++q) { ra[q] = RT<Real>::mk2(row_a[2 * q], row_a[2 * q + 1]); rl[q] = RT<Real>::mk2(row_l[2 * q], row_l[2 * q + 1]); }
     }
-    if (!obs_direct || !adj_direct || ND != 8) {
+    if (!obs_direct || !adj_direct || T::NODE_STAGED) {
       if (GMPE_COOP_BULK_STORE) fence_async_smem();
       __syncwarp();
       if (!obs_direct && g_obs) copy_span<Real, N * F>(g_obs, obs_region, nwv * N * F, all_worlds, wmask, lane);
       if (!adj_direct && g_adj) copy_span<Real, EE>(g_adj, adj_region, nwv * EE, all_worlds, wmask, lane);
-      if (ND != 8 && g_nodew) copy_span<Real, N * E * ND>(g_nodew, node_region, nwv * N * E * ND, all_worlds, wmask, lane);
+      if (T::NODE_STAGED && g_nodew) copy_span<Real, N * E * ND>(g_nodew, node_region, nwv * N * E * ND, all_worlds, wmask, lane);
       if (GMPE_COOP_BULK_STORE && lane == 0) bulk_commit();
       __syncwarp();
     }
