@@ -96,7 +96,7 @@ template <typename Real>
 static size_t smem_for(const GmpeConfig& c, int wpb, int stage_graph) {
   int E = c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls;
   int F = obs_dim_of(c);
-  return smem_layout<Real>(wpb, c.num_agents, E, c.num_walls, F, stage_graph, nullptr, nullptr);
+  return smem_layout<Real>(wpb, c.num_agents, E, c.num_walls, F, stage_graph, nullptr);
 }
 
 // Small worlds stage the adjacency matrix and the padded edge buffers of a tile in shared

@@ -48,45 +48,60 @@ struct KParams {
 };
 
 // ---- shared memory carve-up --------------------------------------------------------
+// The dynamic shared memory of the tile kernel.  The carve-up is kept as 32-bit OFFSETS into
+// this array, not as pointers: the table does not fit in registers next to everything else,
+// and a pointer that has been through local memory comes back as a generic address -- every
+// access to the tile then went down the global load path (LD.E / ST.E, long-scoreboard
+// stalls) instead of LDS / STS.  An offset added to the array keeps the address space.
+extern __shared__ __align__(32) unsigned char gmpe_tile_smem[];
+
+template <typename T>
+struct SPtr {
+  uint32_t off;
+#ifdef __CUDA_ARCH__
+  __device__ __forceinline__ operator T*() const { return reinterpret_cast<T*>(gmpe_tile_smem + off); }
+#endif
+};
+
 template <typename Real>
 struct Smem {
   // -- live for the whole tile
-  typename RT<Real>::V2* pos;      // [WPB*E]   post-step positions of every entity
-  typename RT<Real>::V2* velpre;   // [WPB*N]   p_vel before reward()
-  typename RT<Real>::V2* velpost;  // [WPB*N]   p_vel after reward() (heading re-draw on goal reach)
-  Real* wf;                        // [WPB*16]
-  Real* wl;                        // [WPB*W*4]
-  int32_t* wstep;                  // [WPB]
-  int32_t* wep;                    // [WPB]
-  uint8_t* stpre;                  // [WPB*N]
-  uint8_t* stpost;                 // [WPB*N]
-  uint8_t* mask;                   // [WPB*E]   entity disconnected from the graph
-  uint8_t* wreset;                 // [WPB]
-  uint8_t* wwrite;                 // [WPB]
+  SPtr<typename RT<Real>::V2> pos;      // [WPB*E]   post-step positions of every entity
+  SPtr<typename RT<Real>::V2> velpre;   // [WPB*N]   p_vel before reward()
+  SPtr<typename RT<Real>::V2> velpost;  // [WPB*N]   p_vel after reward() (heading re-draw on goal reach)
+  SPtr<Real> wf;                        // [WPB*16]
+  SPtr<Real> wl;                        // [WPB*W*4]
+  SPtr<int32_t> wstep;                  // [WPB]
+  SPtr<int32_t> wep;                    // [WPB]
+  SPtr<uint8_t> stpre;                  // [WPB*N]
+  SPtr<uint8_t> stpost;                 // [WPB*N]
+  SPtr<uint8_t> mask;                   // [WPB*E]   entity disconnected from the graph
+  SPtr<uint8_t> wreset;                 // [WPB]
+  SPtr<uint8_t> wwrite;                 // [WPB]
   // -- phase-A scratch (dead once obs has left the SM) ...
-  typename RT<Real>::V4* nst;      // [WPB*N]   reset: freshly placed agent states
-  Real* obs;                       // [WPB*N*F] staging
-  Real* rew;                       // [WPB*N]
-  Real* sperr;                     // [WPB*N]
-  int32_t* cold;                   // [WPB*N*3] info counters before this step
-  int32_t* cnew;                   // [WPB*N*3] ... after
-  uint8_t* done;                   // [WPB*N]
+  SPtr<typename RT<Real>::V4> nst;      // [WPB*N]   reset: freshly placed agent states
+  SPtr<Real> obs;                       // [WPB*N*F] staging
+  SPtr<Real> rew;                       // [WPB*N]
+  SPtr<Real> sperr;                     // [WPB*N]
+  SPtr<int32_t> cold;                   // [WPB*N*3] info counters before this step
+  SPtr<int32_t> cnew;                   // [WPB*N*3] ... after
+  SPtr<uint8_t> done;                   // [WPB*N]
   // -- ... aliased by the phase-B staging of small worlds (KParams::stage_graph)
-  Real* adjs;                      // [WPB*E*E]
-  int32_t* eidx;                   // [WPB*2*cap]
-  Real* eattr;                     // [WPB*cap]
-  int32_t* gidx;                   // [WPB*2*cap]
-  Real* gattr;                     // [WPB*cap]
+  SPtr<Real> adjs;                      // [WPB*E*E]
+  SPtr<int32_t> eidx;                   // [WPB*2*cap]
+  SPtr<Real> eattr;                     // [WPB*cap]
+  SPtr<int32_t> gidx;                   // [WPB*2*cap]
+  SPtr<Real> gattr;                     // [WPB*cap]
   // -- large worlds: per-row edge counts -> exclusive row offsets (row-wise phase B)
-  int32_t* rowoff_env;             // [WPB*E]
-  int32_t* rowoff_gnn;             // [WPB*E]
+  SPtr<int32_t> rowoff_env;             // [WPB*E]
+  SPtr<int32_t> rowoff_gnn;             // [WPB*E]
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // stage_graph: 0 none, bit0 adjacency + env edges, bit1 gnn edges as well
 template <typename Real>
-__host__ __device__ inline size_t smem_layout(int wpb, int N, int E, int W, int F, int stage_graph, Smem<Real>* s, unsigned char* base) {
+__host__ __device__ inline size_t smem_layout(int wpb, int N, int E, int W, int F, int stage_graph, Smem<Real>* s) {
   size_t o = 0;
   auto take = [&](size_t bytes, size_t al) { o = align_up(o, al); size_t r = o; o += bytes; return r; };
   const size_t R = sizeof(Real);
@@ -128,32 +143,32 @@ __host__ __device__ inline size_t smem_layout(int wpb, int N, int E, int W, int 
   }
   if (o < scratch_end) o = scratch_end;
   if (s) {
-    s->pos = (typename RT<Real>::V2*)(base + o_pos);
-    s->velpre = (typename RT<Real>::V2*)(base + o_vpre);
-    s->velpost = (typename RT<Real>::V2*)(base + o_vpost);
-    s->wf = (Real*)(base + o_wf);
-    s->wl = (Real*)(base + o_wl);
-    s->wstep = (int32_t*)(base + o_wstep);
-    s->wep = (int32_t*)(base + o_wep);
-    s->stpre = base + o_stpre;
-    s->stpost = base + o_stpost;
-    s->mask = base + o_mask;
-    s->wreset = base + o_wreset;
-    s->wwrite = base + o_wwrite;
-    s->rowoff_env = (int32_t*)(base + o_ro_env);
-    s->rowoff_gnn = (int32_t*)(base + o_ro_gnn);
-    s->nst = (typename RT<Real>::V4*)(base + o_nst);
-    s->obs = (Real*)(base + o_obs);
-    s->rew = (Real*)(base + o_rew);
-    s->sperr = (Real*)(base + o_sp);
-    s->cold = (int32_t*)(base + o_cold);
-    s->cnew = (int32_t*)(base + o_cnew);
-    s->done = base + o_done;
-    s->adjs = (Real*)(base + o_adjs);
-    s->eidx = (int32_t*)(base + o_eidx);
-    s->eattr = (Real*)(base + o_eattr);
-    s->gidx = (int32_t*)(base + o_gidx);
-    s->gattr = (Real*)(base + o_gattr);
+    s->pos.off = (uint32_t)o_pos;
+    s->velpre.off = (uint32_t)o_vpre;
+    s->velpost.off = (uint32_t)o_vpost;
+    s->wf.off = (uint32_t)o_wf;
+    s->wl.off = (uint32_t)o_wl;
+    s->wstep.off = (uint32_t)o_wstep;
+    s->wep.off = (uint32_t)o_wep;
+    s->stpre.off = (uint32_t)o_stpre;
+    s->stpost.off = (uint32_t)o_stpost;
+    s->mask.off = (uint32_t)o_mask;
+    s->wreset.off = (uint32_t)o_wreset;
+    s->wwrite.off = (uint32_t)o_wwrite;
+    s->rowoff_env.off = (uint32_t)o_ro_env;
+    s->rowoff_gnn.off = (uint32_t)o_ro_gnn;
+    s->nst.off = (uint32_t)o_nst;
+    s->obs.off = (uint32_t)o_obs;
+    s->rew.off = (uint32_t)o_rew;
+    s->sperr.off = (uint32_t)o_sp;
+    s->cold.off = (uint32_t)o_cold;
+    s->cnew.off = (uint32_t)o_cnew;
+    s->done.off = (uint32_t)o_done;
+    s->adjs.off = (uint32_t)o_adjs;
+    s->eidx.off = (uint32_t)o_eidx;
+    s->eattr.off = (uint32_t)o_eattr;
+    s->gidx.off = (uint32_t)o_gidx;
+    s->gattr.off = (uint32_t)o_gattr;
   }
   return align_up(o, 16);
 }
@@ -549,7 +564,6 @@ template <typename Real, int NC = 0, int LC = 0, int OC = 0, int WC = 0, int SC 
 __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_kernel(const __grid_constant__ KParams p) {
   using V2 = typename RT<Real>::V2;
   using V4 = typename RT<Real>::V4;
-  extern __shared__ __align__(32) unsigned char smem_raw[];
   const GmpeConfig& c = p.c;
   const int N = NC ? NC : c.num_agents, L = NC ? LC : c.num_landmarks, O = NC ? OC : c.num_obstacles, W = NC ? WC : c.num_walls;
   const int E = NC ? NC + LC + OC + WC : p.E, F = p.F;
@@ -566,7 +580,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
   const bool do_info = (c.flags & GMPE_FLAG_INFO) != 0;
   const int tid = threadIdx.x, nthr = blockDim.x;
   Smem<Real> sm;
-  smem_layout<Real>(WPB, N, E, W, F, p.stage_graph, &sm, smem_raw);
+  smem_layout<Real>(WPB, N, E, W, F, p.stage_graph, &sm);
 
   Real* g_as = (Real*)p.st.agent_state;
   Real* g_aux = (Real*)p.st.agent_aux;
