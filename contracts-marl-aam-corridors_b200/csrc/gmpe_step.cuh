@@ -550,6 +550,10 @@ __device__ __forceinline__ void masked_dist4(const typename RT<Real>::V2* pw, co
 // Launch bounds picked by tools/sweep.py on a B200 (profiles/r1_sweep.txt): 128 threads with
 // >= 7 resident CTAs per SM (<= 72 registers) beat 256 x 1..4 and 128 x 3..6, 8 on the large-world
 // workloads (latency-bound: resident warps matter more than the extra spills).
+#ifndef GMPE_EDGE_UNROLL
+#define GMPE_EDGE_UNROLL 2
+#endif
+constexpr int kEdgeUnroll = GMPE_EDGE_UNROLL;
 #ifndef GMPE_LB_THREADS
 #define GMPE_LB_THREADS 128
 #endif
@@ -1127,7 +1131,9 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
     } else if (!rowwise) {
       // ---- mid-size worlds (or reset-only launches of small ones): element-parallel, in place
       // adj: masked distance matrix, one copy per world (july:1625-1648)
-      if (p.out.adj) {
+      // (when an edge list is emitted as well, its pass below computes every distance anyway
+      // and writes the adjacency row-major as it goes)
+      if (p.out.adj && !(env_e || gnn_e)) {
         Real* g_adj = (Real*)p.out.adj + (size_t)w0 * EE;
         const int total = nw * EE;
         for (int q = tid; q < total; q += nthr) {
@@ -1153,7 +1159,9 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           Real* ea = env_e ? (Real*)p.out.edge_attr + gb * cap : nullptr;
           int32_t* gi = gnn_e ? p.out.gnn_edge_index + gb * 2 * cap : nullptr;
           Real* gea = gnn_e ? (Real*)p.out.gnn_edge_attr + gb * cap : nullptr;
+          Real* g_adjw = p.out.adj ? (Real*)p.out.adj + gb * EE : nullptr;
           int n_env = 0, n_gnn = 0;
+#pragma unroll kEdgeUnroll
           for (int base = 0; base < EE; base += 32) {
             int q = base + lane;
             uint32_t r = 0, cc = 0;
@@ -1162,6 +1170,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
               dE.divmod(q, r, cc);
               V2 a = pw[r], bb = pw[cc];
               d = (r == cc || mk[r] || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
+              if (g_adjw) g_adjw[q] = d;  // masked distance matrix, one copy per world (july:1625-1648)
             }
             if (env_e) {  // update_graph: (d <= max_edge_dist) & (d > 0), row-major (july:1660-1665)
               bool on = d > Real(0) && d <= thr_env;

@@ -35,6 +35,13 @@ def run(args):
     return subprocess.run(["ncu", "-i"] + args, capture_output=True, text=True).stdout
 
 
+def num(x):
+    try:
+        return int(x)
+    except (TypeError, ValueError):
+        return 0
+
+
 def main(rep, src_path):
     rows = list(csv.reader(io.StringIO(run([rep, "--page", "raw", "--csv"]))))
     H = rows[0]
@@ -70,7 +77,7 @@ def main(rep, src_path):
             except ValueError:
                 continue
             d = dict(zip(Hh[4:], r[4:]))
-            out.append((cur, ln, int(d.get("Instructions Executed") or 0), int(d.get("# Samples") or 0), r[1][:100]))
+            out.append((cur, ln, num(d.get("Instructions Executed")), num(d.get("# Samples")), r[1][:100]))
     tot = sum(o[2] for o in out) or 1
     ts = sum(o[3] for o in out) or 1
     reg = {}
