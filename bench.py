@@ -52,6 +52,17 @@ WORKLOADS = {
                   world_size=3, episode_length=75, goal_rew=30, collision_rew=5, formation_rew=1,
                   collaborative=False, use_dones=False, max_speed=2),
         worlds_per_gpu=131072),
+    # ... at the shapes of the reference's eval commands (eval_scripts/commands_test_run.txt:7,30)
+    "two_phase_air_taxi_n5": dict(
+        args=dict(scenario_name="two_phase_graph", dynamics_type="air_taxi", num_agents=5, num_landmarks=5,
+                  world_size=3, episode_length=100, goal_rew=20, collision_rew=20, collaborative=False, use_dones=False,
+                  max_speed=2),
+        worlds_per_gpu=65536),
+    "three_phase_air_taxi_n10": dict(
+        args=dict(scenario_name="three_phase_graph", dynamics_type="air_taxi", num_agents=10, num_landmarks=10,
+                  world_size=4, episode_length=150, goal_rew=20, collision_rew=20, collaborative=False, use_dones=False,
+                  max_speed=2),
+        worlds_per_gpu=32768),
     # BASELINE.json configs[3]
     "navigation_graph_n16_o8_w4": dict(
         args=dict(scenario_name="navigation_graph", dynamics_type="double_integrator", num_agents=16,

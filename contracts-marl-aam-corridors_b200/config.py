@@ -202,8 +202,9 @@ def validate(c: abi.GmpeConfig) -> None:
         raise ValueError(f"too many entities (max {abi.MAX_ENTITIES})")
     if L < N:
         raise ValueError("num_landmarks must be >= num_agents (landmark_poses[agent.id], july:1740)")
-    if c.scenario in abi.ROT_INV_SCENARIOS and not (N == 3 and L == 3 and O == 0 and W == 0):
-        raise ValueError("the rot-inv scenarios are served for num_agents == num_landmarks == 3 without obstacles / walls")
+    if c.scenario in abi.ROT_INV_SCENARIOS and not (N in abi.ROT_INV_AGENT_COUNTS and L == N and O == 0 and W == 0):
+        raise ValueError(f"the rot-inv scenarios are served for num_agents == num_landmarks in {abi.ROT_INV_AGENT_COUNTS} "
+                         "without obstacles / walls")
     if c.scenario in abi.ROT_INV_SCENARIOS and c.physics != abi.PHYS_KINEMATIC:
         raise ValueError("the rot-inv scenarios use the kinematic step")
     if c.scenario == abi.SCEN_JULY_TUBE and (O or W):

@@ -83,7 +83,9 @@ struct CoopTraits {
   static constexpr int ROUND_B = EIDX_BYTES + EATTR_BYTES;
   // Bulk stores read the slab asynchronously: rounds A and B get separate regions when the
   // resident CTAs still fit in shared memory, else they share one and B waits for A to drain.
-  static constexpr int MINBLOCKS = R == 4 ? GMPE_COOP_MINBLOCKS_F32 : GMPE_COOP_MINBLOCKS_F64;
+  // resident CTAs asked of the compiler: the register budget has to grow with the per-lane
+  // world image (positions, goals, velocities and two distance rows of 2N entries)
+  static constexpr int MINBLOCKS = N > 5 ? (R == 4 ? 2 : 1) : (N > 3 ? (R == 4 ? 3 : 2) : (R == 4 ? GMPE_COOP_MINBLOCKS_F32 : GMPE_COOP_MINBLOCKS_F64));
   static constexpr bool SPLIT = GMPE_COOP_BULK_STORE && (up16(ROUND_A + ROUND_B) + 0) * GMPE_COOP_WARPS * MINBLOCKS <= 220 * 1024;
   static constexpr int B_OFF = SPLIT ? ROUND_A : 0;
   static constexpr int SLAB_BYTES = SPLIT ? up16(ROUND_A + ROUND_B) : up16(ROUND_A > ROUND_B ? ROUND_A : ROUND_B);
@@ -136,7 +138,7 @@ template <typename Real>
 __device__ __forceinline__ Real shfl_(Real v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 template <typename Real, int SCEN, int N>
-__global__ void __launch_bounds__(32 * GMPE_COOP_WARPS, sizeof(Real) == 4 ? GMPE_COOP_MINBLOCKS_F32 : GMPE_COOP_MINBLOCKS_F64)
+__global__ void __launch_bounds__(32 * GMPE_COOP_WARPS, CoopTraits<Real, SCEN, N>::MINBLOCKS)
 gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
   using V2 = typename RT<Real>::V2;
   using V4 = typename RT<Real>::V4;

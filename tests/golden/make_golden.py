@@ -323,6 +323,11 @@ def main():
     run_july_trace(g("two_phase_n3_pursuit_s31.npz"), seed=31, T=150, policy="pursuit", scenario_name="two_phase_graph")
     run_july_trace(g("two_phase_n3_pursuit_s32_ep2.npz"), seed=32, T=110, policy="pursuit", eps=0.3, episodes=2,
                    scenario_name="two_phase_graph")
+    # the shapes of the reference's eval commands (eval_scripts/commands_test_run.txt:7,30)
+    run_july_trace(g("two_phase_n5_pursuit_s33.npz"), seed=33, T=100, policy="pursuit", scenario_name="two_phase_graph",
+                   num_agents=5, num_landmarks=5, world_size=3)
+    run_july_trace(g("three_phase_n10_pursuit_s24.npz"), seed=24, T=150, policy="pursuit", scenario_name="three_phase_graph",
+                   num_agents=10, num_landmarks=10, world_size=4)
     # ... and nav_graph_metered_single_corridor_rot_inv.py (model_weights/tube/rot_inv/airtaxi)
     run_july_trace(g("corridor_rot_inv_n3_pursuit_s41.npz"), seed=41, T=150, policy="pursuit",
                    scenario_name="nav_graph_metered_single_corridor_rot_inv")

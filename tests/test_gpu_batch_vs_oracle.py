@@ -37,6 +37,16 @@ CASES = {
                                            B=300, T=20),
     "two_phase_n3": dict(args=dict(scenario_name="two_phase_graph", dynamics_type="air_taxi", world_size=3,
                                    episode_length=12, goal_rew=30, collaborative=False), B=1000, T=30),
+    # the reference's eval command shapes (eval_scripts/commands_test_run.txt:7,30)
+    "two_phase_n5": dict(args=dict(scenario_name="two_phase_graph", dynamics_type="air_taxi", world_size=3, num_agents=5,
+                                   num_landmarks=5, episode_length=12, goal_rew=20, collision_rew=20, collaborative=False),
+                         B=500, T=30),
+    "three_phase_n10": dict(args=dict(scenario_name="three_phase_graph", dynamics_type="air_taxi", world_size=4, num_agents=10,
+                                      num_landmarks=10, episode_length=12, goal_rew=20, collision_rew=20, collaborative=False),
+                            B=300, T=30),
+    "corridor_rot_inv_n5": dict(args=dict(scenario_name="nav_graph_metered_single_corridor_rot_inv", dynamics_type="air_taxi",
+                                          world_size=3, num_agents=5, num_landmarks=5, episode_length=25, goal_rew=30,
+                                          collaborative=False), B=300, T=30),
     "corridor_rot_inv_n3": dict(args=dict(scenario_name="nav_graph_metered_single_corridor_rot_inv", dynamics_type="air_taxi",
                                           world_size=3, episode_length=25, goal_rew=30, collaborative=False), B=1000, T=30),
     "july_di_kinematic": dict(args=dict(scenario_name="nav_metered_one_goal_graph_rotate_tube_july",
@@ -51,6 +61,22 @@ def _cfg(case, precision):
     kw = dict(CASES[case].get("kw", {}))
     return make_config(default_args(**CASES[case]["args"]), CASES[case]["B"], precision=precision, seed=7,
                        world_offset=3, gnn_edges=True, **kw)
+
+
+def _neighbour_ties(state, eps=1e-5):
+    """Worlds where some agent's nearest-neighbour ranking (the "two nearest agents" of the
+    observation, july:1399-1415, tp:1182-1196) hangs on a distance gap below fp32 resolution:
+    either order is a correct fp32 answer, so those worlds are left out of the real-valued
+    comparison for that step."""
+    P = state["agent_state"][..., :2]
+    n = P.shape[1]
+    if n < 3:
+        return np.zeros(P.shape[0], dtype=bool)
+    D = np.linalg.norm(P[:, :, None] - P[:, None, :], axis=-1)
+    D[:, np.arange(n), np.arange(n)] = np.inf
+    S = np.sort(D, axis=-1)
+    gaps = np.diff(S[..., :min(3, n - 1)], axis=-1)
+    return (gaps < eps).any(axis=(1, 2))
 
 
 def _actions(cfg, T, seed):
@@ -132,7 +158,7 @@ def test_fp32_teacher_forced_per_step(case):
         for k in INT_OUT:
             ne = (g[k].cpu().numpy() != o[k]).reshape(cfg64.num_worlds, -1).any(axis=1)
             bad_worlds |= ne
-        ok = ~bad_worlds
+        ok = ~bad_worlds & ~_neighbour_ties(orc.state)
         for k in REAL_OUT:
             a = g[k].cpu().numpy().astype(np.float64)[ok]
             b = o[k][ok]
