@@ -31,6 +31,14 @@ MARKS_SMALL = [("copy helpers", "warp-cooperative slab -> global copies"), ("pla
                ("edges", "emission: edge lists"), ("node_obs", "emission: node features")]
 
 
+MARKS_COOP = [("copy helpers", "Contiguous span of n elements"), ("prologue", "gmpe_step_coop_kernel(const"),
+              ("loads", "loads: one agent per lane"), ("physics", "stage 2 + stage 1: action decode"),
+              ("passA", "pass A: what reward()"), ("passB", "pass B: terms that look at other agents"),
+              ("reward/done/info out", "reward / done / info outputs"), ("state write-back", "state write-back ----"),
+              ("reset", "reset (auto-reset of finished worlds, or MODE_RESET)"), ("node_obs", "emission: node features"),
+              ("obs+adj", "emission: obs rows + adjacency"), ("edges", "emission: edge lists")]
+
+
 def run(args):
     return subprocess.run(["ncu", "-i"] + args, capture_output=True, text=True).stdout
 
@@ -56,7 +64,7 @@ def main(rep, src_path):
                                             "--launch-count", "1"]))))
     src = open(src_path).read().split("\n")
     marks = []
-    for name, needle in (MARKS_SMALL if 'small' in src_path else MARKS_TILE):
+    for name, needle in (MARKS_SMALL if 'small' in src_path else (MARKS_COOP if 'coop' in src_path else MARKS_TILE)):
         for i, l in enumerate(src):
             if needle in l:
                 marks.append((name, i + 1))
