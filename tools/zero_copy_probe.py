@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Does it pay to let the step kernel write the host-facing outputs (obs, node_obs, adj, reward,
+done) straight into pinned host memory over PCIe instead of HBM + a D2H copy?  Run under gpurun."""
+import ctypes as C
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gmpe_b200  # noqa: E402,F401
+from gmpe_b200 import abi, buffers, default_args, make_config  # noqa: E402
+from gmpe_b200.engine import BatchedGraphMPE  # noqa: E402
+
+B = int(os.environ.get("PROBE_B", 65536))
+args = default_args(scenario_name="navigation_graph", num_agents=3, num_landmarks=3, episode_length=25, collaborative=True)
+cfg = make_config(args, B, precision="fp32", seed=1)
+eng = BatchedGraphMPE(cfg, 0)
+eng.reset()
+act = torch.randint(0, 5, (B, 3), dtype=torch.int32, device="cuda")
+names = ("obs", "node_obs", "adj", "reward", "done")
+pinned = {k: torch.empty_like(eng.out[k], device="cpu").pin_memory() for k in names}
+nbytes = sum(t.numel() * t.element_size() for t in pinned.values())
+merged = dict(eng.out)
+merged.update(pinned)
+host_struct = buffers.make_struct(abi.GmpeStepOut, merged)
+
+
+def timed(fn, n=30):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / n * 1e3
+
+
+def device_then_copy():
+    eng.step(act)
+    for k in names:
+        pinned[k].copy_(eng.out[k], non_blocking=True)
+
+
+def straight_to_host():
+    eng.step(act, out_struct=host_struct)
+
+
+print(f"{B} worlds, {nbytes / 1e6:.1f} MB of host-facing outputs per step")
+print(f"step into HBM + 5 D2H copies : {timed(device_then_copy):.3f} ms")
+print(f"step writing to pinned host  : {timed(straight_to_host):.3f} ms")
+eng.step(act)
+ref = {k: eng.out[k].cpu() for k in names}
+eng2 = BatchedGraphMPE(cfg, 0)
+eng2.reset()
+eng2.step(act, out_struct=host_struct)
+torch.cuda.synchronize()
+print("same bytes:", all(torch.equal(ref[k], pinned[k]) for k in names))
