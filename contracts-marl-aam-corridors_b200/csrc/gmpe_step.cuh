@@ -934,7 +934,10 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           pos_w[N + L + O + q] = dst[0] == Real(0) ? RT<Real>::mk2(mid, dst[1]) : RT<Real>::mk2(dst[1], mid);
         }
       } else {
-        place_world<Real>(p, sm, lw, b);
+        // the out-of-line reset gets a COPY of the offset table: were `sm` itself to escape, it
+        // would live in local memory and every hot loop would reload its offsets (LDL) per iteration
+        const Smem<Real> sm_reset = sm;
+        place_world<Real>(p, sm_reset, lw, b);
       }
       // persist the world-level arrays
       Real* wf = sm.wf + lw * GMPE_WORLD_F;
@@ -1147,9 +1150,16 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           g_adj[q] = (r == cc || mk[r] || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
         }
       }
-      // edges: warp-per-world stream compaction (ballot + popc) into the padded buffers
+      // edges + adjacency: a warp walks the rows of one world.  Every lane keeps its (up to two)
+      // columns -- position and mask of entities `lane` and `lane + 32` -- in registers for the
+      // whole world, the row entity is a shared-memory broadcast, so a row costs two distance
+      // evaluations per lane and no index arithmetic; each pair distance is evaluated once and
+      // feeds the adjacency entry and the stream compaction (ballot + popc, row-major order:
+      // columns < 32 first) into the padded buffers.
       if (env_e || gnn_e) {
         const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+        const unsigned lt = (1u << lane) - 1u;
+        const bool two = E > 32;
         for (int w = warp; w < nw; w += nwarps) {
           if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
           const V2* pw = sm.pos + w * E;
@@ -1159,37 +1169,59 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           Real* ea = env_e ? (Real*)p.out.edge_attr + gb * cap : nullptr;
           int32_t* gi = gnn_e ? p.out.gnn_edge_index + gb * 2 * cap : nullptr;
           Real* gea = gnn_e ? (Real*)p.out.gnn_edge_attr + gb * cap : nullptr;
-          Real* g_adjw = p.out.adj ? (Real*)p.out.adj + gb * EE : nullptr;
+          Real* g_adjw = p.out.adj ? (Real*)p.out.adj + gb * EE : nullptr;  // masked distance matrix, one copy per world (july:1625-1648)
+          const int c0 = lane, c1 = lane + 32;
+          const bool h0 = c0 < E, h1 = two && c1 < E;
+          const V2 b0 = pw[h0 ? c0 : 0], b1 = pw[h1 ? c1 : 0];
+          const bool off0 = !h0 || mk[h0 ? c0 : 0] != 0, off1 = !h1 || mk[h1 ? c1 : 0] != 0;
           int n_env = 0, n_gnn = 0;
 #pragma unroll kEdgeUnroll
-          for (int base = 0; base < EE; base += 32) {
-            int q = base + lane;
-            uint32_t r = 0, cc = 0;
-            Real d = Real(0);
-            if (q < EE) {
-              dE.divmod(q, r, cc);
-              V2 a = pw[r], bb = pw[cc];
-              d = (r == cc || mk[r] || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
-              if (g_adjw) g_adjw[q] = d;  // masked distance matrix, one copy per world (july:1625-1648)
+          for (int r = 0; r < E; ++r) {
+            const V2 a = pw[r];
+            const bool mr = mk[r] != 0;
+            const Real d0 = (mr || off0 || r == c0) ? Real(0) : norm2(a.x - b0.x, a.y - b0.y);
+            const Real d1 = (mr || off1 || r == c1) ? Real(0) : norm2(a.x - b1.x, a.y - b1.y);
+            if (g_adjw) {
+              if (h0) g_adjw[r * E + c0] = d0;
+              if (h1) g_adjw[r * E + c1] = d1;
             }
             if (env_e) {  // update_graph: (d <= max_edge_dist) & (d > 0), row-major (july:1660-1665)
-              bool on = d > Real(0) && d <= thr_env;
-              unsigned m = __ballot_sync(0xffffffffu, on);
-              if (on) {
-                int slot = n_env + __popc(m & ((1u << lane) - 1));
-                ei[slot] = (int32_t)r; ei[cap + slot] = (int32_t)cc; ea[slot] = d;
+              const bool on0 = d0 > Real(0) && d0 <= thr_env;
+              const unsigned m0 = __ballot_sync(0xffffffffu, on0);
+              if (on0) {
+                const int slot = n_env + __popc(m0 & lt);
+                ei[slot] = r; ei[cap + slot] = c0; ea[slot] = d0;
               }
-              n_env += __popc(m);
+              n_env += __popc(m0);
+              if (two) {
+                const bool on1 = d1 > Real(0) && d1 <= thr_env;
+                const unsigned m1 = __ballot_sync(0xffffffffu, on1);
+                if (on1) {
+                  const int slot = n_env + __popc(m1 & lt);
+                  ei[slot] = r; ei[cap + slot] = c1; ea[slot] = d1;
+                }
+                n_env += __popc(m1);
+              }
             }
             if (gnn_e) {  // process_adj on the fp32 cast: (adj < max_edge_dist) & (adj > 0) (gnn_new.py:339)
-              float df = (float)d;
-              bool on = df > 0.0f && df < thr_gnn;
-              unsigned m = __ballot_sync(0xffffffffu, on);
-              if (on) {
-                int slot = n_gnn + __popc(m & ((1u << lane) - 1));
-                gi[slot] = (int32_t)r; gi[cap + slot] = (int32_t)cc; gea[slot] = Real(df);
+              const float f0 = (float)d0;
+              const bool on0 = f0 > 0.0f && f0 < thr_gnn;
+              const unsigned m0 = __ballot_sync(0xffffffffu, on0);
+              if (on0) {
+                const int slot = n_gnn + __popc(m0 & lt);
+                gi[slot] = r; gi[cap + slot] = c0; gea[slot] = Real(f0);
               }
-              n_gnn += __popc(m);
+              n_gnn += __popc(m0);
+              if (two) {
+                const float f1 = (float)d1;
+                const bool on1 = f1 > 0.0f && f1 < thr_gnn;
+                const unsigned m1 = __ballot_sync(0xffffffffu, on1);
+                if (on1) {
+                  const int slot = n_gnn + __popc(m1 & lt);
+                  gi[slot] = r; gi[cap + slot] = c1; gea[slot] = Real(f1);
+                }
+                n_gnn += __popc(m1);
+              }
             }
           }
           if (env_e) {
