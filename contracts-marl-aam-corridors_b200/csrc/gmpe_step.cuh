@@ -92,9 +92,6 @@ struct Smem {
   SPtr<Real> eattr;                     // [WPB*cap]
   SPtr<int32_t> gidx;                   // [WPB*2*cap]
   SPtr<Real> gattr;                     // [WPB*cap]
-  // -- large worlds: per-row edge counts -> exclusive row offsets (row-wise phase B)
-  SPtr<int32_t> rowoff_env;             // [WPB*E]
-  SPtr<int32_t> rowoff_gnn;             // [WPB*E]
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -118,8 +115,6 @@ __host__ __device__ inline size_t smem_layout(int wpb, int N, int E, int W, int 
   size_t o_mask = take(wpb * E, 16);
   size_t o_wreset = take(wpb, 16);
   size_t o_wwrite = take(wpb, 16);
-  size_t o_ro_env = take(4 * wpb * E, 16);
-  size_t o_ro_gnn = take(4 * wpb * E, 16);
   o = align_up(o, 32);
   const size_t scratch0 = o;
   size_t o_nst = take(4 * R * wpb * N, 32);
@@ -155,8 +150,6 @@ __host__ __device__ inline size_t smem_layout(int wpb, int N, int E, int W, int 
     s->mask.off = (uint32_t)o_mask;
     s->wreset.off = (uint32_t)o_wreset;
     s->wwrite.off = (uint32_t)o_wwrite;
-    s->rowoff_env.off = (uint32_t)o_ro_env;
-    s->rowoff_gnn.off = (uint32_t)o_ro_gnn;
     s->nst.off = (uint32_t)o_nst;
     s->obs.off = (uint32_t)o_obs;
     s->rew.off = (uint32_t)o_rew;
@@ -531,19 +524,6 @@ __device__ __forceinline__ void pad_edges(int32_t* ei, Real* ea, int n, int cap,
   fill_span<int32_t>(ei, -1, n, cap, lane);
   fill_span<int32_t>(ei + cap, -1, n, cap, lane);
   fill_span<Real>(ea, Real(0), n, cap, lane);
-}
-
-// Four consecutive entries of a masked distance row (july:1625-1648): columns cb .. cb+3 of row r.
-template <typename Real>
-__device__ __forceinline__ void masked_dist4(const typename RT<Real>::V2* pw, const uint8_t* mk, typename RT<Real>::V2 a, bool mr,
-                                             int r, int cb, Real (&d)[4]) {
-  using V4 = typename RT<Real>::V4;
-  const V4 p01 = *reinterpret_cast<const V4*>(pw + cb), p23 = *reinterpret_cast<const V4*>(pw + cb + 2);
-  const uint32_t m4 = *reinterpret_cast<const uint32_t*>(mk + cb);
-  d[0] = (r == cb || mr || (m4 & 0xffu)) ? Real(0) : norm2(a.x - p01.x, a.y - p01.y);
-  d[1] = (r == cb + 1 || mr || (m4 & 0xff00u)) ? Real(0) : norm2(a.x - p01.z, a.y - p01.w);
-  d[2] = (r == cb + 2 || mr || (m4 & 0xff0000u)) ? Real(0) : norm2(a.x - p23.x, a.y - p23.y);
-  d[3] = (r == cb + 3 || mr || (m4 & 0xff000000u)) ? Real(0) : norm2(a.x - p23.z, a.y - p23.w);
 }
 
 // ---- the kernel ----------------------------------------------------------------------
@@ -1131,7 +1111,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
         copy_out<int32_t>(p.out.gnn_edge_index + (size_t)w0 * 2 * cap, sm.gidx, nw * 2 * cap, tid, nthr);
         copy_out<Real>((Real*)p.out.gnn_edge_attr + (size_t)w0 * cap, sm.gattr, nw * cap, tid, nthr);
       }
-    } else if (!rowwise) {
+    } else {
       // ---- mid-size worlds (or reset-only launches of small ones): element-parallel, in place
       // adj: masked distance matrix, one copy per world (july:1625-1648)
       // (when an edge list is emitted as well, its pass below computes every distance anyway
@@ -1159,7 +1139,8 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
       if (env_e || gnn_e) {
         const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
         const unsigned lt = (1u << lane) - 1u;
-        const bool two = E > 32;
+        constexpr int MAXG = (GMPE_MAX_ENTITIES + 31) / 32;  // column groups of 32 entities
+        const int ng = (E + 31) >> 5;
         for (int w = warp; w < nw; w += nwarps) {
           if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
           const V2* pw = sm.pos + w * E;
@@ -1170,57 +1151,45 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           int32_t* gi = gnn_e ? p.out.gnn_edge_index + gb * 2 * cap : nullptr;
           Real* gea = gnn_e ? (Real*)p.out.gnn_edge_attr + gb * cap : nullptr;
           Real* g_adjw = p.out.adj ? (Real*)p.out.adj + gb * EE : nullptr;  // masked distance matrix, one copy per world (july:1625-1648)
-          const int c0 = lane, c1 = lane + 32;
-          const bool h0 = c0 < E, h1 = two && c1 < E;
-          const V2 b0 = pw[h0 ? c0 : 0], b1 = pw[h1 ? c1 : 0];
-          const bool off0 = !h0 || mk[h0 ? c0 : 0] != 0, off1 = !h1 || mk[h1 ? c1 : 0] != 0;
+          V2 bcol[MAXG];
+          uint32_t offm = 0, has = 0;  // bit g: the lane's column of group g is masked / exists
+#pragma unroll
+          for (int g = 0; g < MAXG; ++g) {
+            const int cg = lane + 32 * g;
+            const bool h = g < ng && cg < E;
+            bcol[g] = pw[h ? cg : 0];
+            has |= (uint32_t)h << g;
+            offm |= (uint32_t)(!h || mk[h ? cg : 0] != 0) << g;
+          }
           int n_env = 0, n_gnn = 0;
 #pragma unroll kEdgeUnroll
           for (int r = 0; r < E; ++r) {
             const V2 a = pw[r];
             const bool mr = mk[r] != 0;
-            const Real d0 = (mr || off0 || r == c0) ? Real(0) : norm2(a.x - b0.x, a.y - b0.y);
-            const Real d1 = (mr || off1 || r == c1) ? Real(0) : norm2(a.x - b1.x, a.y - b1.y);
-            if (g_adjw) {
-              if (h0) g_adjw[r * E + c0] = d0;
-              if (h1) g_adjw[r * E + c1] = d1;
-            }
-            if (env_e) {  // update_graph: (d <= max_edge_dist) & (d > 0), row-major (july:1660-1665)
-              const bool on0 = d0 > Real(0) && d0 <= thr_env;
-              const unsigned m0 = __ballot_sync(0xffffffffu, on0);
-              if (on0) {
-                const int slot = n_env + __popc(m0 & lt);
-                ei[slot] = r; ei[cap + slot] = c0; ea[slot] = d0;
-              }
-              n_env += __popc(m0);
-              if (two) {
-                const bool on1 = d1 > Real(0) && d1 <= thr_env;
-                const unsigned m1 = __ballot_sync(0xffffffffu, on1);
-                if (on1) {
-                  const int slot = n_env + __popc(m1 & lt);
-                  ei[slot] = r; ei[cap + slot] = c1; ea[slot] = d1;
+#pragma unroll
+            for (int g = 0; g < MAXG; ++g) {
+              if (g >= ng) break;  // uniform
+              const int cg = lane + 32 * g;
+              const Real d = (mr || ((offm >> g) & 1u) || r == cg) ? Real(0) : norm2(a.x - bcol[g].x, a.y - bcol[g].y);
+              if (g_adjw && ((has >> g) & 1u)) g_adjw[r * E + cg] = d;
+              if (env_e) {  // update_graph: (d <= max_edge_dist) & (d > 0), row-major (july:1660-1665)
+                const bool on = d > Real(0) && d <= thr_env;
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) {
+                  const int slot = n_env + __popc(m & lt);
+                  ei[slot] = r; ei[cap + slot] = cg; ea[slot] = d;
                 }
-                n_env += __popc(m1);
+                n_env += __popc(m);
               }
-            }
-            if (gnn_e) {  // process_adj on the fp32 cast: (adj < max_edge_dist) & (adj > 0) (gnn_new.py:339)
-              const float f0 = (float)d0;
-              const bool on0 = f0 > 0.0f && f0 < thr_gnn;
-              const unsigned m0 = __ballot_sync(0xffffffffu, on0);
-              if (on0) {
-                const int slot = n_gnn + __popc(m0 & lt);
-                gi[slot] = r; gi[cap + slot] = c0; gea[slot] = Real(f0);
-              }
-              n_gnn += __popc(m0);
-              if (two) {
-                const float f1 = (float)d1;
-                const bool on1 = f1 > 0.0f && f1 < thr_gnn;
-                const unsigned m1 = __ballot_sync(0xffffffffu, on1);
-                if (on1) {
-                  const int slot = n_gnn + __popc(m1 & lt);
-                  gi[slot] = r; gi[cap + slot] = c1; gea[slot] = Real(f1);
+              if (gnn_e) {  // process_adj on the fp32 cast: (adj < max_edge_dist) & (adj > 0) (gnn_new.py:339)
+                const float df = (float)d;
+                const bool on = df > 0.0f && df < thr_gnn;
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) {
+                  const int slot = n_gnn + __popc(m & lt);
+                  gi[slot] = r; gi[cap + slot] = cg; gea[slot] = Real(df);
                 }
-                n_gnn += __popc(m1);
+                n_gnn += __popc(m);
               }
             }
           }
@@ -1231,171 +1200,6 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           if (gnn_e) {
             for (int q = n_gnn + lane; q < cap; q += 32) { gi[q] = -1; gi[cap + q] = -1; gea[q] = Real(0); }
             if (lane == 0) p.out.gnn_num_edges[gb] = n_gnn;
-          }
-        }
-      }
-    } else {
-      // ---- large worlds (E >= 64): row-wise.  Pass 1 writes the masked distance row (july:1625-1648,
-      // one copy per world) and counts the row's edges; a shuffle scan turns the
-      // counts into row offsets; pass 2 recomputes the row and stream-compacts it (ballot +
-      // popc within the row's lane group) into the fixed-capacity buffers in row-major order
-      // (update_graph july:1660-1665; process_adj gnn_new.py:339).
-      const unsigned grp_mask = LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u);
-      const unsigned lt_mask = (1u << sl) - 1u;
-      const int nrows = nw * E;
-      const bool vec4 = (E & 3) == 0;
-      for (int row0 = warp * rpw; row0 < nrows; row0 += nwarps * rpw) {
-        const int row = row0 + sub;
-        uint32_t w = 0, r = 0;
-        bool live = row < nrows;
-        if (live) { dE.divmod(row, w, r); live = p.mode == MODE_STEP || sm.wwrite[w]; }
-        const V2* pw = sm.pos + w * E;
-        const uint8_t* mk = sm.mask + w * E;
-        const V2 a = pw[r];
-        const bool mr = mk[r] != 0;
-        Real* g_row = (live && p.out.adj) ? (Real*)p.out.adj + ((size_t)(w0 + w) * E + r) * E : nullptr;
-        int n_env = 0, n_gnn = 0;
-        if (vec4) {
-          // E % 4 == 0: a lane owns 4 consecutive columns -- two 128-bit position loads, one
-          // 32-bit mask load and one 128-bit adjacency store per 4 entries
-          for (int c0 = 0; c0 < E; c0 += 128) {
-            const int cb = c0 + 4 * lane;
-            if (live && cb < E) {
-              Real d[4];
-              masked_dist4<Real>(pw, mk, a, mr, (int)r, cb, d);
-              if (g_row) *reinterpret_cast<V4*>(g_row + cb) = RT<Real>::mk4(d[0], d[1], d[2], d[3]);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                n_env += (d[q] > Real(0) && d[q] <= thr_env);
-                const float df = (float)d[q];
-                n_gnn += (df > 0.0f && df < thr_gnn);
-              }
-            }
-          }
-          n_env = __reduce_add_sync(0xffffffffu, n_env);
-          n_gnn = __reduce_add_sync(0xffffffffu, n_gnn);
-        } else {
-          for (int c0 = 0; c0 < E; c0 += LPR) {
-            const int cc = c0 + sl;
-            Real d = Real(0);
-            if (live && cc < E) {
-              const V2 bb = pw[cc];
-              d = ((int)r == cc || mr || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
-              if (g_row) g_row[cc] = d;
-            }
-            if (env_e) n_env += __popc((__ballot_sync(0xffffffffu, d > Real(0) && d <= thr_env) >> (sub * LPR)) & grp_mask);
-            if (gnn_e) { const float df = (float)d; n_gnn += __popc((__ballot_sync(0xffffffffu, df > 0.0f && df < thr_gnn) >> (sub * LPR)) & grp_mask); }
-          }
-        }
-        if (live && sl == 0) { sm.rowoff_env[row] = n_env; sm.rowoff_gnn[row] = n_gnn; }
-      }
-      if (env_e || gnn_e) {
-        __syncthreads();
-        for (int w = warp; w < nw; w += nwarps) {  // exclusive scan of the row counts, per world
-          if (p.mode != MODE_STEP && !sm.wwrite[w]) continue;
-          int run_env = 0, run_gnn = 0;
-          for (int r0 = 0; r0 < E; r0 += 32) {
-            const int r = r0 + lane;
-            const int ve_ = r < E ? sm.rowoff_env[w * E + r] : 0, vg_ = r < E ? sm.rowoff_gnn[w * E + r] : 0;
-            int ie = ve_, ig = vg_;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const int te = __shfl_up_sync(0xffffffffu, ie, o), tg = __shfl_up_sync(0xffffffffu, ig, o);
-              if (lane >= o) { ie += te; ig += tg; }
-            }
-            if (r < E) { sm.rowoff_env[w * E + r] = run_env + ie - ve_; sm.rowoff_gnn[w * E + r] = run_gnn + ig - vg_; }
-            run_env += __shfl_sync(0xffffffffu, ie, 31);
-            run_gnn += __shfl_sync(0xffffffffu, ig, 31);
-          }
-          const size_t gb = (size_t)(w0 + w);
-          // -1 / 0 padding behind the last edge
-          if (env_e) {
-            int32_t* ei = p.out.edge_index + gb * 2 * cap;
-            Real* ea = (Real*)p.out.edge_attr + gb * cap;
-            pad_edges<Real>(ei, ea, run_env, cap, lane);
-            if (lane == 0) p.out.num_edges[gb] = run_env;
-          }
-          if (gnn_e) {
-            int32_t* gi = p.out.gnn_edge_index + gb * 2 * cap;
-            Real* gea = (Real*)p.out.gnn_edge_attr + gb * cap;
-            pad_edges<Real>(gi, gea, run_gnn, cap, lane);
-            if (lane == 0) p.out.gnn_num_edges[gb] = run_gnn;
-          }
-        }
-        __syncthreads();
-        for (int row0 = warp * rpw; row0 < nrows; row0 += nwarps * rpw) {
-          const int row = row0 + sub;
-          uint32_t w = 0, r = 0;
-          bool live = row < nrows;
-          if (live) { dE.divmod(row, w, r); live = p.mode == MODE_STEP || sm.wwrite[w]; }
-          const V2* pw = sm.pos + w * E;
-          const uint8_t* mk = sm.mask + w * E;
-          const V2 a = pw[r];
-          const bool mr = mk[r] != 0;
-          const size_t gb = (size_t)(w0 + w);
-          int32_t* ei = env_e ? p.out.edge_index + gb * 2 * cap : nullptr;
-          Real* ea = env_e ? (Real*)p.out.edge_attr + gb * cap : nullptr;
-          int32_t* gi = gnn_e ? p.out.gnn_edge_index + gb * 2 * cap : nullptr;
-          Real* gea = gnn_e ? (Real*)p.out.gnn_edge_attr + gb * cap : nullptr;
-          int b_env = live ? sm.rowoff_env[row] : 0, b_gnn = live ? sm.rowoff_gnn[row] : 0;
-          if (vec4) {
-            for (int c0 = 0; c0 < E; c0 += 128) {
-              const int cb = c0 + 4 * lane;
-              Real d[4] = {Real(0), Real(0), Real(0), Real(0)};
-              if (live && cb < E) masked_dist4<Real>(pw, mk, a, mr, (int)r, cb, d);
-#pragma unroll 1
-              for (int pass = 0; pass < 2; ++pass) {
-                if (!(pass == 0 ? env_e : gnn_e)) continue;
-                unsigned bits = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float df = (float)d[q];
-                  const bool on = pass == 0 ? (d[q] > Real(0) && d[q] <= thr_env) : (df > 0.0f && df < thr_gnn);
-                  bits |= (unsigned)on << q;
-                }
-                const int cnt = __popc(bits);
-                int inc = cnt;  // inclusive scan of the per-lane counts: columns are ordered by lane, then q
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                  const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                  if (lane >= o) inc += t;
-                }
-                int& base = pass == 0 ? b_env : b_gnn;
-                int slot = base + inc - cnt;
-                base += __shfl_sync(0xffffffffu, inc, 31);
-                int32_t* xi = pass == 0 ? ei : gi;
-                Real* xa = pass == 0 ? ea : gea;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  if ((bits >> q) & 1u) {
-                    xi[slot] = (int32_t)r; xi[cap + slot] = cb + q;
-                    xa[slot] = pass == 0 ? d[q] : Real((float)d[q]);
-                    ++slot;
-                  }
-              }
-            }
-            continue;
-          }
-          for (int c0 = 0; c0 < E; c0 += LPR) {
-            const int cc = c0 + sl;
-            Real d = Real(0);
-            if (live && cc < E) {
-              const V2 bb = pw[cc];
-              d = ((int)r == cc || mr || mk[cc]) ? Real(0) : norm2(a.x - bb.x, a.y - bb.y);
-            }
-            if (env_e) {
-              const bool on = d > Real(0) && d <= thr_env;
-              const unsigned m = (__ballot_sync(0xffffffffu, on) >> (sub * LPR)) & grp_mask;
-              if (on) { const int slot = b_env + __popc(m & lt_mask); ei[slot] = (int32_t)r; ei[cap + slot] = cc; ea[slot] = d; }
-              b_env += __popc(m);
-            }
-            if (gnn_e) {
-              const float df = (float)d;
-              const bool on = df > 0.0f && df < thr_gnn;
-              const unsigned m = (__ballot_sync(0xffffffffu, on) >> (sub * LPR)) & grp_mask;
-              if (on) { const int slot = b_gnn + __popc(m & lt_mask); gi[slot] = (int32_t)r; gi[cap + slot] = cc; gea[slot] = Real(df); }
-              b_gnn += __popc(m);
-            }
           }
         }
       }
