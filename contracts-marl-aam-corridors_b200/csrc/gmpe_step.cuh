@@ -530,6 +530,12 @@ __device__ __forceinline__ void pad_edges(int32_t* ei, Real* ea, int n, int cap,
 // Launch bounds picked by tools/sweep.py on a B200 (profiles/r1_sweep.txt): 128 threads with
 // >= 7 resident CTAs per SM (<= 72 registers) beat 256 x 1..4 and 128 x 3..6, 8 on the large-world
 // workloads (latency-bound: resident warps matter more than the extra spills).
+#ifndef GMPE_TILE_NODE_ROWWISE_MIN_E  // node rows: warp per (world, ego) from this many entities on
+#define GMPE_TILE_NODE_ROWWISE_MIN_E 64
+#endif
+#ifndef GMPE_XSKIP  // experiments only (tools/ab.py): bit0 edge stores, bit1 adj stores, bit2 node rows, bit3 padding
+#define GMPE_XSKIP 0
+#endif
 #ifndef GMPE_EDGE_UNROLL
 #define GMPE_EDGE_UNROLL 2
 #endif
@@ -998,7 +1004,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
     // walk the entities, so the inner loops carry no index arithmetic.  (Measured on B200:
     // 951 -> 746 us at E = 128; for E = 44 sub-warp row groups of 16 lanes were slower than
     // the element-parallel form below, 461 vs 382 us, so smaller worlds keep that.)
-    const bool rowwise = !p.stage_graph && E >= 64;
+    const bool rowwise = !p.stage_graph && E >= GMPE_TILE_NODE_ROWWISE_MIN_E;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     constexpr int LPR = 32, rpw = 1;
     const int sub = 0, sl = lane;
@@ -1043,11 +1049,11 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           const V2 vk = (k <= j ? sm.velpost : sm.velpre)[w * N + k];
           const V2 gk = pw[N + k];  // landmark_poses[entity.id] (july:1740)
           const Real f[8] = {vk.x - ve.x, vk.y - ve.y, rx, ry, gk.x - pe.x, gk.y - pe.y, Real(0), Real(0)};
-          store_row8(g_node + (size_t)q * 8, f);
+          if (!(GMPE_XSKIP & 4)) store_row8(g_node + (size_t)q * 8, f);
         } else {
           const Real ty = k < (uint32_t)(N + L) ? Real(1) : (k < (uint32_t)(N + L + O) ? Real(2) : Real(3));
           const Real f[8] = {Real(0) - ve.x, Real(0) - ve.y, rx, ry, rx, ry, Real(1), ty};
-          store_row8(g_node + (size_t)q * 8, f);
+          if (!(GMPE_XSKIP & 4)) store_row8(g_node + (size_t)q * 8, f);
         }
       }
     }
@@ -1171,11 +1177,11 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
               if (g >= ng) break;  // uniform
               const int cg = lane + 32 * g;
               const Real d = (mr || ((offm >> g) & 1u) || r == cg) ? Real(0) : norm2(a.x - bcol[g].x, a.y - bcol[g].y);
-              if (g_adjw && ((has >> g) & 1u)) g_adjw[r * E + cg] = d;
+              if (!(GMPE_XSKIP & 2) && g_adjw && ((has >> g) & 1u)) g_adjw[r * E + cg] = d;
               if (env_e) {  // update_graph: (d <= max_edge_dist) & (d > 0), row-major (july:1660-1665)
                 const bool on = d > Real(0) && d <= thr_env;
                 const unsigned m = __ballot_sync(0xffffffffu, on);
-                if (on) {
+                if (on && !(GMPE_XSKIP & 1)) {
                   const int slot = n_env + __popc(m & lt);
                   ei[slot] = r; ei[cap + slot] = cg; ea[slot] = d;
                 }
@@ -1194,7 +1200,8 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
             }
           }
           if (env_e) {
-            for (int q = n_env + lane; q < cap; q += 32) { ei[q] = -1; ei[cap + q] = -1; ea[q] = Real(0); }
+            if (!(GMPE_XSKIP & 8))
+              for (int q = n_env + lane; q < cap; q += 32) { ei[q] = -1; ei[cap + q] = -1; ea[q] = Real(0); }
             if (lane == 0) p.out.num_edges[gb] = n_env;
           }
           if (gnn_e) {
