@@ -22,6 +22,8 @@ from __future__ import annotations
 from abc import ABC, abstractmethod
 from typing import Optional
 
+import os
+
 import numpy as np
 import torch
 
@@ -207,6 +209,8 @@ class _BatchedVecEnv(ShareVecEnv):
         # copies run on their own stream while slice k+1's host->device copy and kernel proceed.
         if pipeline_chunks is None:
             pipeline_chunks = 4 if (output == "numpy" and B >= 8192) else 1
+            if os.environ.get("GMPE_PIPELINE_CHUNKS"):  # tuning knob
+                pipeline_chunks = int(os.environ["GMPE_PIPELINE_CHUNKS"])
         self._chunks = max(1, int(pipeline_chunks))
         self._s_in = torch.cuda.Stream(device=dev)
         self._s_out = torch.cuda.Stream(device=dev)
@@ -244,7 +248,11 @@ class _BatchedVecEnv(ShareVecEnv):
         step = -(-step // 64) * 64  # slices start on multiples of 64 worlds: every slab stays 16-byte aligned
         return [(b0, min(B, b0 + step)) for b0 in range(0, B, step)]
 
-    def _step_pipelined(self, pinned_actions: torch.Tensor, dev_actions: torch.Tensor, onehot: bool):
+    def _step_pipelined(self, pinned_actions: torch.Tensor, dev_actions: torch.Tensor, onehot: bool,
+                        src: torch.Tensor | None = None):
+        """The batch in slices: while slice k is stepped and its outputs go back over PCIe, the host
+        already stages slice k+1 of the caller's action block (``src``, pageable) into pinned
+        memory and sends it up."""
         eng = self.engine
         cur = torch.cuda.current_stream(eng.device)
         self._s_in.wait_stream(cur)
@@ -252,6 +260,8 @@ class _BatchedVecEnv(ShareVecEnv):
         arena = self._arena[self._flip]
         self._flip ^= 1
         for b0, b1 in self._bounds():
+            if src is not None:
+                pinned_actions[b0:b1].copy_(src[b0:b1])  # torch's threaded copy: ~15x a numpy assignment
             with torch.cuda.stream(self._s_in):
                 dev_actions[b0:b1].copy_(pinned_actions[b0:b1], non_blocking=True)
                 ev_in = torch.cuda.Event()
@@ -338,13 +348,14 @@ class _BatchedVecEnv(ShareVecEnv):
                 w = 8 if a.dtype == np.float64 else 4
                 if a.dtype not in (np.float64, np.float32):
                     a = a.astype(np.float32)
-                # torch's threaded copy fills the pinned block ~15x faster than a numpy assignment
-                self._act_pin[w].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+                src = torch.from_numpy(np.ascontiguousarray(a))
                 self.h2d_bytes_last = a.size * w
                 if self._chunks > 1:
-                    self._step_pipelined(self._act_pin[w], self._act_dev[w], onehot=True)
+                    self._step_pipelined(self._act_pin[w], self._act_dev[w], onehot=True, src=src)
                     self.waiting = True
                     return
+                # torch's threaded copy fills the pinned block ~15x faster than a numpy assignment
+                self._act_pin[w].copy_(src)
                 self._act_dev[w].copy_(self._act_pin[w], non_blocking=True)
                 idx = eng.decode_onehot(self._act_dev[w])
         eng.step(idx)
