@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # error codes
 OK, E_INVALID, E_CUDA, E_NULL = 0, -1, -2, -3
@@ -112,7 +112,7 @@ class GmpeStepInject(C.Structure):
 EXPORTED_SYMBOLS = (
     "gmpe_abi_version", "gmpe_create", "gmpe_destroy", "gmpe_last_error", "gmpe_layout",
     "gmpe_reset", "gmpe_step", "gmpe_decode_onehot", "gmpe_launch_count", "gmpe_set_seed",
-    "gmpe_kernel_name", "gmpe_step_range", "gmpe_decode_onehot_range",
+    "gmpe_kernel_name", "gmpe_step_range", "gmpe_decode_onehot_range", "gmpe_step_host", "gmpe_host_wait",
 )
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -158,6 +158,11 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.gmpe_step_range.restype = C.c_int
     lib.gmpe_decode_onehot_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.gmpe_decode_onehot_range.restype = C.c_int
+    lib.gmpe_step_host.argtypes = [C.c_void_p, C.POINTER(GmpeState), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(GmpeStepOut), C.POINTER(GmpeStepOut), C.c_int, C.c_void_p]
+    lib.gmpe_step_host.restype = C.c_int
+    lib.gmpe_host_wait.argtypes = [C.c_void_p]
+    lib.gmpe_host_wait.restype = C.c_int
     lib.gmpe_launch_count.argtypes = [C.c_void_p]
     lib.gmpe_launch_count.restype = C.c_int64
     lib.gmpe_kernel_name.argtypes = [C.c_void_p]

@@ -6,6 +6,9 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
+#include <utility>
+#include <algorithm>
 
 #include "gmpe_coop.cuh"
 #include "gmpe_small.cuh"
@@ -29,6 +32,9 @@ struct gmpe_ctx {
   void* act_tab;  // device copy of the _set_action table (Real [32][2]); the only memory the library owns
   int64_t launches;
   std::string err;
+  // gmpe_step_host: copy streams and per-slice events, created on first use
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev;
 };
 
 static thread_local std::string g_create_err;
@@ -363,11 +369,14 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
 
 int gmpe_destroy(gmpe_handle h) {
   if (!h) return GMPE_E_NULL;
-  if (h->act_tab) {
+  {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(h->device);
-    cudaFree(h->act_tab);
+    if (h->act_tab) cudaFree(h->act_tab);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     cudaSetDevice(prev);
   }
   delete h;
@@ -504,6 +513,93 @@ int gmpe_decode_onehot_range(gmpe_handle h, const void* onehot, int elem_bytes, 
   if (prev != h->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("decode_onehot launch failed: ") + cudaGetErrorString(e));
   h->launches += 1;
+  return GMPE_OK;
+}
+
+// Slices of the batch for gmpe_step_host: multiples of 64 worlds (every slab of a slice stays
+// 16-byte aligned); the first slice is a quarter of the others -- nothing flows back over PCIe
+// until it has been staged, sent up and stepped.
+static std::vector<std::pair<int64_t, int64_t>> host_slices(int64_t B, int k) {
+  std::vector<std::pair<int64_t, int64_t>> out;
+  const int64_t al = 64;
+  if (k < 1 || B < 64 * al) k = 1;
+  if (k == 1) { out.push_back({0, B}); return out; }
+  int64_t first = (B / (4 * k - 3)) / al * al;
+  if (first < al) first = al;
+  int64_t step = (B - first + (k - 2)) / (k - 1);
+  step = (step + al - 1) / al * al;
+  out.push_back({0, first});
+  for (int64_t b0 = first; b0 < B; b0 += step) out.push_back({b0, std::min(B, b0 + step) - b0});
+  return out;
+}
+
+int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host, int action_kind, void* actions_pinned,
+                   void* actions_dev, int32_t* idx_dev, const GmpeStepOut* dev_out, const GmpeStepOut* host_out, int slices,
+                   void* cuda_stream) {
+  if (!h) return GMPE_E_NULL;
+  if (!st || !actions_host || !actions_pinned || !actions_dev || !dev_out || !host_out)
+    return fail(h, GMPE_E_NULL, "gmpe_step_host: NULL argument");
+  if (action_kind != 0 && action_kind != 4 && action_kind != 8) return fail(h, GMPE_E_INVALID, "gmpe_step_host: action_kind must be 0, 4 or 8");
+  if (action_kind != 0 && !idx_dev) return fail(h, GMPE_E_NULL, "gmpe_step_host: idx_dev is NULL");
+  const GmpeConfig& c = h->cfg;
+  const int64_t B = c.num_worlds, N = c.num_agents, E = N + c.num_landmarks + c.num_obstacles + c.num_walls, cap = E * (E - 1);
+  const int64_t R = c.precision == GMPE_F64 ? 8 : 4, F = obs_dim_of(c), ND = node_dim_of(c);
+  const int64_t act_bpw = action_kind == 0 ? N * 4 : N * (int64_t)c.total_actions * action_kind;  // bytes per world
+  // GmpeStepOut is fifteen pointers in declaration order: bytes per world of each
+  const int64_t bpw[15] = {N * F * R, N * E * ND * R, E * E * R, N * R, N, N * GMPE_INFO_K * R, 2 * cap * 4, cap * R, 4,
+                           2 * cap * 4, cap * R, 4, N * R, N * 4, N * 4};
+  static_assert(sizeof(GmpeStepOut) == 15 * sizeof(void*), "GmpeStepOut layout");
+  void* const* dptr = reinterpret_cast<void* const*>(dev_out);
+  void* const* hptr = reinterpret_cast<void* const*>(host_out);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  cudaStream_t main_s = (cudaStream_t)cuda_stream;
+  const auto sl = host_slices(B, slices);
+  cudaError_t e = cudaSuccess;
+  if (!h->s_in) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess && !h->s_out) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+  while (e == cudaSuccess && h->ev.size() < 2 * sl.size() + 1) {
+    cudaEvent_t v;
+    e = cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
+    if (e == cudaSuccess) h->ev.push_back(v);
+  }
+  int rc = GMPE_OK;
+  if (e == cudaSuccess) {  // the copy-in stream starts behind whatever the caller has queued on its stream
+    e = cudaEventRecord(h->ev[2 * sl.size()], main_s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_in, h->ev[2 * sl.size()], 0);
+  }
+  for (size_t k = 0; k < sl.size() && e == cudaSuccess && rc == GMPE_OK; ++k) {
+    const int64_t b0 = sl[k].first, cnt = sl[k].second;
+    const int64_t off = b0 * act_bpw, nb = cnt * act_bpw;
+    if (actions_pinned != actions_host) memcpy((char*)actions_pinned + off, (const char*)actions_host + off, (size_t)nb);
+    e = cudaMemcpyAsync((char*)actions_dev + off, (const char*)actions_pinned + off, (size_t)nb, cudaMemcpyHostToDevice, h->s_in);
+    if (e == cudaSuccess) e = cudaEventRecord(h->ev[2 * k], h->s_in);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(main_s, h->ev[2 * k], 0);
+    if (e != cudaSuccess) break;
+    const int32_t* idx = action_kind == 0 ? (const int32_t*)actions_dev : idx_dev;
+    if (action_kind != 0) rc = gmpe_decode_onehot_range(h, actions_dev, action_kind, idx_dev, b0, cnt, cuda_stream);
+    if (rc == GMPE_OK) rc = launch(h, MODE_STEP, st, idx, nullptr, nullptr, dev_out, cuda_stream, b0, cnt);
+    if (rc != GMPE_OK) break;
+    cudaSetDevice(h->device);  // (the calls above restore the caller's device)
+    e = cudaEventRecord(h->ev[2 * k + 1], main_s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_out, h->ev[2 * k + 1], 0);
+    for (int f = 0; f < 15 && e == cudaSuccess; ++f)
+      if (dptr[f] && hptr[f])
+        e = cudaMemcpyAsync((char*)hptr[f] + b0 * bpw[f], (const char*)dptr[f] + b0 * bpw[f], (size_t)(cnt * bpw[f]),
+                            cudaMemcpyDeviceToHost, h->s_out);
+  }
+  if (prev != h->device) cudaSetDevice(prev);
+  if (rc != GMPE_OK) return rc;
+  if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("gmpe_step_host: ") + cudaGetErrorString(e));
+  return GMPE_OK;
+}
+
+int gmpe_host_wait(gmpe_handle h) {
+  if (!h) return GMPE_E_NULL;
+  if (!h->s_out) return GMPE_OK;
+  cudaError_t e = cudaStreamSynchronize(h->s_out);
+  if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("gmpe_host_wait: ") + cudaGetErrorString(e));
   return GMPE_OK;
 }
 

@@ -167,6 +167,22 @@ class BatchedGraphMPE:
                                       C.byref(self._out), begin, count, s)
         self._check(rc, "gmpe_step_range")
 
+    def step_host(self, actions_host: torch.Tensor, actions_pinned: torch.Tensor, actions_dev: torch.Tensor,
+                  host_out: "abi.GmpeStepOut", slices: int) -> None:
+        """One host-facing step (gmpe_step_host): ``actions_host`` -- a CPU tensor, int32 (B, N) indices
+        or float32 / float64 (B, N, A) one-hot -- is staged, sent up, decoded and stepped slice by slice,
+        and every output that ``host_out`` names is copied back into its pinned tensor; copies and
+        kernels of neighbouring slices overlap.  Returns once enqueued: call :meth:`host_wait`."""
+        kind = 0 if actions_host.dtype == torch.int32 else actions_host.element_size()
+        rc = self.lib.gmpe_step_host(self._h, C.byref(self._st), actions_host.data_ptr(), kind, actions_pinned.data_ptr(),
+                                     actions_dev.data_ptr(), self.action_idx.data_ptr(), C.byref(self._out), C.byref(host_out),
+                                     int(slices), self._stream())
+        self._check(rc, "gmpe_step_host")
+        self._keep = (actions_host, actions_pinned, actions_dev, host_out)
+
+    def host_wait(self) -> None:
+        self._check(self.lib.gmpe_host_wait(self._h), "gmpe_host_wait")
+
     def decode_onehot(self, onehot: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """argmax of the runner's one-hot actions (environment.py:431,444) on device."""
         A = self.cfg.total_actions

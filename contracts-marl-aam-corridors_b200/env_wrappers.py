@@ -27,7 +27,7 @@ import os
 import numpy as np
 import torch
 
-from . import abi
+from . import abi, buffers
 from .config import make_config
 from .engine import BatchedGraphMPE
 from .environment import build_spaces
@@ -212,11 +212,11 @@ class _BatchedVecEnv(ShareVecEnv):
             if os.environ.get("GMPE_PIPELINE_CHUNKS"):  # tuning knob
                 pipeline_chunks = int(os.environ["GMPE_PIPELINE_CHUNKS"])
         self._chunks = max(1, int(pipeline_chunks))
-        self._s_in = torch.cuda.Stream(device=dev)
-        self._s_out = torch.cuda.Stream(device=dev)
         self._host_names = [n for n in ("obs", "node_obs", "adj", "reward", "done", "indiv_reward", "info")
                             if n in self.engine.out_slabs and not (self._lazy_info and n in ("indiv_reward", "info"))]
         self._host_t = [self._host_tensors(a) for a in self._arena]
+        # the same pinned views as a GmpeStepOut of host pointers, for gmpe_step_host
+        self._host_struct = [buffers.make_struct(abi.GmpeStepOut, t) for t in self._host_t]
         self._pending = None
 
     # -- host views of the pinned arena ---------------------------------------------------
@@ -242,47 +242,20 @@ class _BatchedVecEnv(ShareVecEnv):
             out[n] = arena[off:off + nb].view(ref.dtype).view(ref.shape)
         return out
 
-    def _bounds(self):
-        B, k = self.num_envs, self._chunks
-        step = -(-B // k)
-        step = -(-step // 64) * 64  # slices start on multiples of 64 worlds: every slab stays 16-byte aligned
-        return [(b0, min(B, b0 + step)) for b0 in range(0, B, step)]
-
-    def _step_pipelined(self, pinned_actions: torch.Tensor, dev_actions: torch.Tensor, onehot: bool,
-                        src: torch.Tensor | None = None):
-        """The batch in slices: while slice k is stepped and its outputs go back over PCIe, the host
-        already stages slice k+1 of the caller's action block (``src``, pageable) into pinned
-        memory and sends it up."""
-        eng = self.engine
-        cur = torch.cuda.current_stream(eng.device)
-        self._s_in.wait_stream(cur)
-        host = self._host_t[self._flip]
-        arena = self._arena[self._flip]
+    def _step_pipelined(self, src: torch.Tensor, pinned_actions: torch.Tensor, dev_actions: torch.Tensor):
+        """The batch in slices through ONE library call (gmpe_step_host): while slice k is stepped and
+        its outputs go back over PCIe, slice k+1 of the caller's action block (``src``, pageable) is
+        staged into pinned memory and sent up.  The copies of the results are in flight on return."""
+        self.engine.step_host(src, pinned_actions, dev_actions, self._host_struct[self._flip], self._chunks)
+        self._pending = self._arena[self._flip]
         self._flip ^= 1
-        for b0, b1 in self._bounds():
-            if src is not None:
-                pinned_actions[b0:b1].copy_(src[b0:b1])  # torch's threaded copy: ~15x a numpy assignment
-            with torch.cuda.stream(self._s_in):
-                dev_actions[b0:b1].copy_(pinned_actions[b0:b1], non_blocking=True)
-                ev_in = torch.cuda.Event()
-                ev_in.record(self._s_in)
-            cur.wait_event(ev_in)
-            eng.step_range(eng.action_idx if onehot else dev_actions, b0, b1 - b0, stream=cur,
-                           onehot=dev_actions if onehot else None)
-            ev_k = torch.cuda.Event()
-            ev_k.record(cur)
-            self._s_out.wait_event(ev_k)
-            with torch.cuda.stream(self._s_out):
-                for n in self._host_names:
-                    host[n][b0:b1].copy_(eng.out[n][b0:b1], non_blocking=True)
-        self._pending = arena
 
     def _fetch(self):
         if self.output == "torch":
             return dict(self.engine.out)
         if self._pending is not None:  # a pipelined step already has its copies in flight
             arena, self._pending = self._pending, None
-            self._s_out.synchronize()
+            self.engine.host_wait()
             self._last_arena = arena
             return self._host_views(arena)
         arena = self._arena[self._flip]
@@ -351,7 +324,7 @@ class _BatchedVecEnv(ShareVecEnv):
                 src = torch.from_numpy(np.ascontiguousarray(a))
                 self.h2d_bytes_last = a.size * w
                 if self._chunks > 1:
-                    self._step_pipelined(self._act_pin[w], self._act_dev[w], onehot=True, src=src)
+                    self._step_pipelined(src, self._act_pin[w], self._act_dev[w])
                     self.waiting = True
                     return
                 # torch's threaded copy fills the pinned block ~15x faster than a numpy assignment

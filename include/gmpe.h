@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GMPE_ABI_VERSION 9
+#define GMPE_ABI_VERSION 10
 
 /* error codes */
 #define GMPE_OK 0
@@ -283,6 +283,26 @@ int gmpe_decode_onehot(gmpe_handle h, const void* onehot, int elem_bytes,
 /* ... for a slice of worlds (whole-batch pointers, as gmpe_step_range). */
 int gmpe_decode_onehot_range(gmpe_handle h, const void* onehot, int elem_bytes, int32_t* action_idx,
                              int64_t world_begin, int64_t world_count, void* cuda_stream);
+
+/* GraphSubprocVecEnv.step (onpolicy/envs/env_wrappers.py:959-1004) for a caller whose actions
+ * and results live in HOST memory: the batch is cut into `slices` (the first one shorter, so
+ * that results start to flow early) and for every slice the library stages the caller's action
+ * block into page-locked memory, sends it up, decodes + steps the slice (gmpe_decode_onehot_range
+ * + gmpe_step_range) and copies the slice of every field that is non-NULL in BOTH dev_out and
+ * host_out back -- host->device copy, kernels and device->host copy of neighbouring slices
+ * overlap on streams the handle owns.  The call returns when everything is ENQUEUED;
+ * gmpe_host_wait blocks until the results are in host_out.  One host step in flight per handle.
+ *   actions_host   [B][N] int32 indices (action_kind 0) or [B][N][A] one-hot float / double
+ *                  (action_kind 4 / 8), pageable or page-locked;
+ *   actions_pinned page-locked staging block of the same size (may equal actions_host when
+ *                  that is page-locked itself: no staging copy then);
+ *   actions_dev    device block of the same size; idx_dev int32 [B][N] device (ignored for
+ *                  action_kind 0, where actions_dev already holds the indices);
+ *   dev_out        device outputs exactly as for gmpe_step; host_out page-locked mirrors. */
+int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host, int action_kind,
+                   void* actions_pinned, void* actions_dev, int32_t* idx_dev, const GmpeStepOut* dev_out,
+                   const GmpeStepOut* host_out, int slices, void* cuda_stream);
+int gmpe_host_wait(gmpe_handle h);
 
 /* Re-key the Philox streams: replaces env.seed(seed) (environment.py:219-223, called by
  * train_mpe.py:31 with seed + rank*1000); world_offset as in GmpeConfig. */
