@@ -15,7 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "libgmpe_b200.so")
 SOURCES = ["gmpe_api.cu"]
-DEPS = ["gmpe_api.cu", "gmpe_step.cuh", "gmpe_device.cuh", os.path.join("..", "..", "include", "gmpe.h")]
+DEPS = ["gmpe_api.cu", "gmpe_step.cuh", "gmpe_small.cuh", "gmpe_coop.cuh", "gmpe_device.cuh",
+        os.path.join("..", "..", "include", "gmpe.h")]
 
 
 def nvcc_path() -> str:

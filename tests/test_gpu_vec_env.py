@@ -208,3 +208,42 @@ def test_lazy_infos_are_fetched_on_access_and_guard_against_stale_reads():
     with pytest.raises(RuntimeError, match="earlier step"):
         first[0][0]["Dist_to_goal"]       # ... and stale by now
     lazy.close(), eager.close()
+
+
+@pytest.mark.parametrize("kind", ["int32", "float32", "float64"])
+def test_step_host_matches_step_for_every_action_encoding(kind):
+    """gmpe_step_host (stage, copy up, decode, step, copy down, slice by slice) against gmpe_step
+    on a twin engine: same bytes in the pinned mirrors, for index and one-hot action blocks."""
+    import ctypes as C
+
+    from gmpe_b200 import buffers
+    from gmpe_b200.engine import BatchedGraphMPE
+
+    B, N, A = 5000, 3, 5
+    cfg = make_config(default_args(scenario_name="navigation_graph", episode_length=4, collaborative=True), B, seed=9)
+    a, b = BatchedGraphMPE(cfg, 0), BatchedGraphMPE(cfg, 0)
+    a.reset(), b.reset()
+    names = ("obs", "node_obs", "adj", "reward", "done")
+    pinned = {k: torch.empty_like(b.out[k], device="cpu").pin_memory() for k in names}
+    host = buffers.make_struct(abi.GmpeStepOut, pinned)
+    rs = np.random.RandomState(2)
+    for t in range(7):  # through two auto-resets
+        idx = rs.randint(A, size=(B, N)).astype(np.int32)
+        if kind == "int32":
+            src = torch.from_numpy(idx)
+            dev = torch.empty((B, N), dtype=torch.int32, device="cuda")
+        else:
+            dt = torch.float32 if kind == "float32" else torch.float64
+            src = torch.from_numpy(np.eye(A)[idx]).to(dt)
+            dev = torch.empty((B, N, A), dtype=dt, device="cuda")
+        pin = torch.empty_like(src).pin_memory()
+        a.step(torch.as_tensor(idx, device="cuda"))
+        b.step_host(src, pin, dev, host, slices=3)
+        b.host_wait()
+        for k in names:
+            assert torch.equal(a.out[k].cpu(), pinned[k]), f"t={t} {k}"
+    # error path: a NULL staging block is refused with the library's message, nothing is launched
+    rc = b.lib.gmpe_step_host(b._h, C.byref(b._st), src.data_ptr(), 4, None, dev.data_ptr(), b.action_idx.data_ptr(),
+                              C.byref(b._out), C.byref(host), 2, None)
+    assert rc == abi.E_NULL and b"NULL" in b.lib.gmpe_last_error(b._h)
+    a.close(), b.close()
