@@ -351,8 +351,10 @@ def run_ours(opts):
     cpu = None
     if world == 1 and not opts.no_cpu:
         cores = os.cpu_count() or 1
-        sample_worlds = min(Bg, 16384)
-        v, done, ms = cpu_leg(wl["args"], sample_worlds, 50, 2, cores, max_seconds=15.0)
+        # bounded sample: the whole batch for up to 400 steps or 10 s of wall time on every host
+        # core (~10-30 core-seconds on the navigation workload), whichever comes first
+        sample_worlds = Bg
+        v, done, ms = cpu_leg(wl["args"], sample_worlds, 400, 2, cores, max_seconds=10.0)
         cpu = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
                "sample": f"{done} steps x {sample_worlds} worlds of the same workload, {cores} pthreads, "
                          "oracle/gmpe_oracle.c (fp64 C port of the reference step); the Python reference itself "
