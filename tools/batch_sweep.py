@@ -11,6 +11,8 @@ SWEEP = {
     "navigation_graph_n3_b65536": (16384, 65536, 262144, 1048576),
     "july_air_taxi_n3_b131072": (32768, 131072, 524288, 1048576),
     "three_phase_air_taxi_n3_b131072": (131072, 524288),
+    "two_phase_air_taxi_n5": (65536, 262144),
+    "three_phase_air_taxi_n10": (32768, 131072),
     "navigation_graph_n16_o8_w4": (4096, 16384, 65536, 262144),
     "july_air_taxi_n64": (1024, 4096, 16384, 32768),
 }
