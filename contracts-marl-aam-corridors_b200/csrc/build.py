@@ -7,6 +7,8 @@ bundled libcudart; the host passes raw device pointers and a cudaStream_t.
 """
 from __future__ import annotations
 
+import concurrent.futures
+import hashlib
 import os
 import shutil
 import subprocess
@@ -14,9 +16,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "libgmpe_b200.so")
-SOURCES = ["gmpe_api.cu"]
-DEPS = ["gmpe_api.cu", "gmpe_step.cuh", "gmpe_small.cuh", "gmpe_coop.cuh", "gmpe_device.cuh",
-        os.path.join("..", "..", "include", "gmpe.h")]
+# one translation unit for the host side + tile / thread-per-world kernels, one per precision for
+# the lane-per-agent kernel instantiations: compiled in parallel, linked into one library
+SOURCES = ["gmpe_api.cu", "gmpe_coop_f32.cu", "gmpe_coop_f64.cu"]
+DEPS = SOURCES + ["gmpe_step.cuh", "gmpe_small.cuh", "gmpe_coop.cuh", "gmpe_device.cuh", "gmpe_coop_table.h",
+                  os.path.join("..", "..", "include", "gmpe.h")]
 
 
 def nvcc_path() -> str:
@@ -42,21 +46,32 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None, de
         OUT_local = OUT
         if not force and not is_stale():
             return OUT
-    cmd = [
-        nvcc_path(), "-std=c++17", "-O3", "-lineinfo",
-        "-gencode", "arch=compute_100a,code=sm_100a",
-        "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
-        "-Xptxas", "-v" if verbose else "-O3",
-        "-o", OUT_local,
-    ] + [f"-D{d}" for d in defines] + [os.path.join(HERE, s) for s in SOURCES]
-    env = dict(os.environ)
+    nvcc = nvcc_path()
+    common = [nvcc, "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3"] + [f"-D{d}" for d in defines]
     if os.path.exists("/usr/bin/g++"):
-        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
-    res = subprocess.run(cmd, cwd=HERE, env=env, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+        common[1:1] = ["-ccbin", "/usr/bin/g++"]
+    tag = hashlib.sha1((OUT_local + "|" + ",".join(defines)).encode()).hexdigest()[:10]
+    objdir = os.path.join(HERE, "..", "..", "build", "obj_" + tag)
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        res = subprocess.run(common + ["-c", os.path.join(HERE, src), "-o", obj], cwd=HERE, capture_output=True, text=True)
+        return src, obj, res
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        done = list(pool.map(compile_one, SOURCES))
+    for src, obj, res in done:
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stderr[-4000:])
+    link = [nvcc] + (["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []) + \
+           ["-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT_local] + [o for _, o, _ in done]
+    res = subprocess.run(link, cwd=HERE, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stderr[-4000:])
+        raise RuntimeError("nvcc link failed:\n" + res.stderr[-4000:])
     return OUT_local
 
 

@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "gmpe_coop.cuh"
+#include "gmpe_coop_table.h"
 #include "gmpe_small.cuh"
 #include "gmpe_step.cuh"
 
@@ -62,9 +63,9 @@ static const char* validate(const GmpeConfig& c) {
   if (c.num_landmarks < c.num_agents) return "num_landmarks must be >= num_agents";
   if (c.num_obstacles < 0 || c.num_walls < 0) return "negative entity count";
   if (c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls > GMPE_MAX_ENTITIES) return "too many entities";
-  if (rot_inv(c) && !((c.num_agents == 3 || c.num_agents == 5 || c.num_agents == 10) && c.num_landmarks == c.num_agents &&
-                      c.num_obstacles == 0 && c.num_walls == 0 && c.physics == GMPE_PHYS_KINEMATIC))
-    return "the rot-inv scenarios are served for num_agents == num_landmarks in {3, 5, 10} without obstacles / walls, kinematic step";
+  if (rot_inv(c) && !(c.num_agents >= COOP_ROT_INV_MIN_AGENTS && c.num_agents <= COOP_ROT_INV_MAX_AGENTS &&
+                      c.num_landmarks == c.num_agents && c.num_obstacles == 0 && c.num_walls == 0 && c.physics == GMPE_PHYS_KINEMATIC))
+    return "the rot-inv scenarios are served for 2 <= num_agents == num_landmarks <= 10 without obstacles / walls, kinematic step";
   if (c.scenario == GMPE_SCEN_JULY_TUBE && (c.num_obstacles || c.num_walls))
     return "july tube scenario supports num_obstacles == num_walls == 0 only (the reference graph builder raises, SURVEY G7)";
   if (c.physics == GMPE_PHYS_FORCE && c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR) return "force physics needs double_integrator state";
@@ -120,7 +121,7 @@ static int pick_stage_graph(const GmpeConfig& c, int wpb) {
 // choice (A/B timing, and the tests that keep every mapping pinned to the oracle).
 enum { KERNEL_TILE = 0, KERNEL_WORLD = 1, KERNEL_COOP = 2 };
 static int pick_kernel(const GmpeConfig& c) {
-  if (rot_inv(c)) return KERNEL_COOP;  // only the lane-per-agent kernel serves that family (N = L in {3, 5, 10})
+  if (rot_inv(c)) return KERNEL_COOP;  // only the lane-per-agent kernel serves that family (2 <= N = L <= 10)
   const bool small = c.num_agents == 3 && c.num_landmarks == 3 && c.num_obstacles == 0 && c.num_walls == 0;
   if (!small) return KERNEL_TILE;
   if (const char* t = getenv("GMPE_FORCE_TILE")) if (atoi(t)) return KERNEL_TILE;
@@ -129,33 +130,6 @@ static int pick_kernel(const GmpeConfig& c) {
     if (!strcmp(k, "world")) return KERNEL_WORLD;
   }
   return KERNEL_COOP;
-}
-
-// lane-per-agent kernel instantiations: N = 3 for every scenario, N = 5 and 10 as well for the
-// rot-inv family (the reference's eval commands run two_phase_graph with 5 and three_phase_graph
-// with 10 agents, eval_scripts/commands_test_run.txt:7,30)
-template <typename Real, int SCEN, int N>
-static void coop_bind(gmpe_ctx* h) {
-  h->fn = (const void*)gmpe_step_coop_kernel<Real, SCEN, N>;
-  h->smem_bytes = GMPE_COOP_WARPS * CoopTraits<Real, SCEN, N>::SLAB_BYTES;
-}
-template <typename Real, int SCEN>
-static void coop_bind_n(gmpe_ctx* h) {
-  switch (h->cfg.num_agents) {
-    case 5: coop_bind<Real, SCEN, 5>(h); break;
-    case 10: coop_bind<Real, SCEN, 10>(h); break;
-    default: coop_bind<Real, SCEN, 3>(h); break;
-  }
-}
-template <typename Real>
-static void coop_bind_scenario(gmpe_ctx* h) {
-  switch (h->cfg.scenario) {
-    case GMPE_SCEN_JULY_TUBE: coop_bind<Real, GMPE_SCEN_JULY_TUBE, 3>(h); break;
-    case GMPE_SCEN_THREE_PHASE: coop_bind_n<Real, GMPE_SCEN_THREE_PHASE>(h); break;
-    case GMPE_SCEN_TWO_PHASE: coop_bind_n<Real, GMPE_SCEN_TWO_PHASE>(h); break;
-    case GMPE_SCEN_CORRIDOR_ROT_INV: coop_bind_n<Real, GMPE_SCEN_CORRIDOR_ROT_INV>(h); break;
-    default: coop_bind<Real, GMPE_SCEN_NAV_GRAPH, 3>(h); break;
-  }
 }
 
 // Persistent grid: at most one wave of resident CTAs, units strided over it.  When the batch
@@ -280,7 +254,14 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
     h->wpb = GMPE_COOP_WARPS * (32 / cfg->num_agents);
     h->num_tiles = (cfg->num_worlds + h->wpb - 1) / h->wpb;
     h->stage_graph = 0;
-    if (f64) coop_bind_scenario<double>(h); else coop_bind_scenario<float>(h);
+    const bool found = f64 ? coop_lookup_f64(cfg->scenario, cfg->num_agents, &h->fn, &h->smem_bytes)
+                           : coop_lookup_f32(cfg->scenario, cfg->num_agents, &h->fn, &h->smem_bytes);
+    if (!found) {
+      cudaSetDevice(prev);
+      const int code = fail(nullptr, GMPE_E_INVALID, "no lane-per-agent kernel for this scenario / num_agents");
+      delete h;
+      return code;
+    }
   } else if (h->small == KERNEL_WORLD) {
     // one thread per world, warps are independent: see gmpe_small.cuh
     h->threads = 32 * GMPE_SMALL_WARPS;

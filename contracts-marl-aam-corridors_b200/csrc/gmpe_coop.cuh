@@ -535,7 +535,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
           dm += cd[k]; tm += ct[k]; sv += Real(nw_ ? n2 : o2);
           if (nw_ && !tp2) dsum += spk;  // tp2 never appends to delta_spacing
         }
-        dm = qdiv(dm, Real(N)); tm = qdiv(tm, Real(N));
+        dm = mean_div(dm, Real(N)); tm = mean_div(tm, Real(N));
         Real ds = Real(0), ts = Real(0);
 #pragma unroll
         for (int k = 0; k < N; ++k) {

@@ -1,0 +1,42 @@
+// Instantiations of gmpe_step_coop_kernel<double, SCEN, N> (see gmpe_coop_table.h).
+#include "gmpe_coop.cuh"
+#include "gmpe_coop_table.h"
+
+namespace gmpe {
+namespace {
+using Real = double;
+
+template <int SCEN, int N>
+void bind(const void** fn, size_t* smem) {
+  *fn = (const void*)gmpe_step_coop_kernel<Real, SCEN, N>;
+  *smem = (size_t)GMPE_COOP_WARPS * CoopTraits<Real, SCEN, N>::SLAB_BYTES;
+}
+
+template <int SCEN>
+bool bind_n(int n, const void** fn, size_t* smem) {
+  switch (n) {
+    case 2: bind<SCEN, 2>(fn, smem); return true;
+    case 3: bind<SCEN, 3>(fn, smem); return true;
+    case 4: bind<SCEN, 4>(fn, smem); return true;
+    case 5: bind<SCEN, 5>(fn, smem); return true;
+    case 6: bind<SCEN, 6>(fn, smem); return true;
+    case 7: bind<SCEN, 7>(fn, smem); return true;
+    case 8: bind<SCEN, 8>(fn, smem); return true;
+    case 9: bind<SCEN, 9>(fn, smem); return true;
+    case 10: bind<SCEN, 10>(fn, smem); return true;
+    default: return false;
+  }
+}
+}  // namespace
+
+bool coop_lookup_f64(int scenario, int n, const void** fn, size_t* smem) {
+  switch (scenario) {
+    case GMPE_SCEN_JULY_TUBE: if (n != 3) return false; bind<GMPE_SCEN_JULY_TUBE, 3>(fn, smem); return true;
+    case GMPE_SCEN_NAV_GRAPH: if (n != 3) return false; bind<GMPE_SCEN_NAV_GRAPH, 3>(fn, smem); return true;
+    case GMPE_SCEN_THREE_PHASE: return bind_n<GMPE_SCEN_THREE_PHASE>(n, fn, smem);
+    case GMPE_SCEN_TWO_PHASE: return bind_n<GMPE_SCEN_TWO_PHASE>(n, fn, smem);
+    case GMPE_SCEN_CORRIDOR_ROT_INV: return bind_n<GMPE_SCEN_CORRIDOR_ROT_INV>(n, fn, smem);
+    default: return false;
+  }
+}
+}  // namespace gmpe

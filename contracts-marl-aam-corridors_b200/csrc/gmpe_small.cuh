@@ -547,7 +547,7 @@ gmpe_step_small_kernel(const __grid_constant__ KParams p) {
           for (int k = 0; k < N; ++k) {
             dm += Real(cnt[k][GMPE_AC_DIST_TRAV_I]); tm += Real(cnt[k][GMPE_AC_TIME_REQ_I]); sv += Real(cnt[k][GMPE_AC_SPACING_VIOL]);
           }
-          dm = qdiv(dm, Real(N)); tm = qdiv(tm, Real(N));
+          dm = mean_div(dm, Real(N)); tm = mean_div(tm, Real(N));
           Real ds = Real(0), ts = Real(0);
 #pragma unroll
           for (int k = 0; k < N; ++k) {

@@ -866,7 +866,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           dm += Real(cc[0]); tm += Real(cc[1]); sv += Real(cc[2]);
           if (k <= (int)i) dsum += sm.sperr[lw * N + k];
         }
-        dm = qdiv(dm, Real(N)); tm = qdiv(tm, Real(N));
+        dm = mean_div(dm, Real(N)); tm = mean_div(tm, Real(N));
         Real ds = Real(0), ts = Real(0);
         for (int k = 0; k < N; ++k) {
           const int32_t* cc = (k <= (int)i ? sm.cnew : sm.cold) + (lw * N + k) * 3;

@@ -328,6 +328,13 @@ def main():
                    num_agents=5, num_landmarks=5, world_size=3)
     run_july_trace(g("three_phase_n10_pursuit_s24.npz"), seed=24, T=150, policy="pursuit", scenario_name="three_phase_graph",
                    num_agents=10, num_landmarks=10, world_size=4)
+    # other agent counts of the family (the lane-per-agent kernel is instantiated for N = 2 .. 10)
+    run_july_trace(g("two_phase_n2_pursuit_s34.npz"), seed=34, T=60, policy="pursuit", scenario_name="two_phase_graph",
+                   num_agents=2, num_landmarks=2, world_size=3)
+    run_july_trace(g("three_phase_n4_pursuit_s25.npz"), seed=25, T=80, policy="pursuit", scenario_name="three_phase_graph",
+                   num_agents=4, num_landmarks=4, world_size=3)
+    run_july_trace(g("corridor_rot_inv_n7_pursuit_s43.npz"), seed=43, T=80, policy="pursuit",
+                   scenario_name="nav_graph_metered_single_corridor_rot_inv", num_agents=7, num_landmarks=7, world_size=4)
     # ... and nav_graph_metered_single_corridor_rot_inv.py (model_weights/tube/rot_inv/airtaxi)
     run_july_trace(g("corridor_rot_inv_n3_pursuit_s41.npz"), seed=41, T=150, policy="pursuit",
                    scenario_name="nav_graph_metered_single_corridor_rot_inv")

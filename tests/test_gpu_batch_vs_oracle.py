@@ -44,6 +44,13 @@ CASES = {
     "three_phase_n10": dict(args=dict(scenario_name="three_phase_graph", dynamics_type="air_taxi", world_size=4, num_agents=10,
                                       num_landmarks=10, episode_length=12, goal_rew=20, collision_rew=20, collaborative=False),
                             B=300, T=30),
+    "two_phase_n2": dict(args=dict(scenario_name="two_phase_graph", dynamics_type="air_taxi", world_size=3, num_agents=2,
+                                   num_landmarks=2, episode_length=12, goal_rew=20, collaborative=False), B=400, T=30),
+    "three_phase_n4": dict(args=dict(scenario_name="three_phase_graph", dynamics_type="air_taxi", world_size=3, num_agents=4,
+                                     num_landmarks=4, episode_length=12, goal_rew=20, collaborative=True), B=400, T=30),
+    "corridor_rot_inv_n7": dict(args=dict(scenario_name="nav_graph_metered_single_corridor_rot_inv", dynamics_type="air_taxi",
+                                          world_size=4, num_agents=7, num_landmarks=7, episode_length=25, goal_rew=30,
+                                          collaborative=False), B=300, T=30),
     "corridor_rot_inv_n5": dict(args=dict(scenario_name="nav_graph_metered_single_corridor_rot_inv", dynamics_type="air_taxi",
                                           world_size=3, num_agents=5, num_landmarks=5, episode_length=25, goal_rew=30,
                                           collaborative=False), B=300, T=30),
