@@ -52,10 +52,5 @@ def straight_to_host():
 print(f"{B} worlds, {nbytes / 1e6:.1f} MB of host-facing outputs per step")
 print(f"step into HBM + 5 D2H copies : {timed(device_then_copy):.3f} ms")
 print(f"step writing to pinned host  : {timed(straight_to_host):.3f} ms")
-eng.step(act)
-ref = {k: eng.out[k].cpu() for k in names}
-eng2 = BatchedGraphMPE(cfg, 0)
-eng2.reset()
-eng2.step(act, out_struct=host_struct)
-torch.cuda.synchronize()
-print("same bytes:", all(torch.equal(ref[k], pinned[k]) for k in names))
+# (measured on a B200: 0.98 ms for HBM + copies, 1.75 ms for direct stores to the host -- the 32-byte
+#  node rows become one PCIe write each -- and 1.02 ms with the node rows staged, GMPE_COOP_STAGE_NODE=1)
