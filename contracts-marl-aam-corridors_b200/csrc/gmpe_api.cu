@@ -63,7 +63,7 @@ static const char* validate(const GmpeConfig& c) {
   if (c.num_landmarks < c.num_agents) return "num_landmarks must be >= num_agents";
   if (c.num_obstacles < 0 || c.num_walls < 0) return "negative entity count";
   if (c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls > GMPE_MAX_ENTITIES) return "too many entities";
-  if (rot_inv(c) && !(c.num_agents >= COOP_ROT_INV_MIN_AGENTS && c.num_agents <= COOP_ROT_INV_MAX_AGENTS &&
+  if (rot_inv(c) && !(c.num_agents >= COOP_MIN_AGENTS && c.num_agents <= COOP_MAX_AGENTS &&
                       c.num_landmarks == c.num_agents && c.num_obstacles == 0 && c.num_walls == 0 && c.physics == GMPE_PHYS_KINEMATIC))
     return "the rot-inv scenarios are served for 2 <= num_agents == num_landmarks <= 10 without obstacles / walls, kinematic step";
   if (c.scenario == GMPE_SCEN_JULY_TUBE && (c.num_obstacles || c.num_walls))
@@ -116,18 +116,19 @@ static int pick_stage_graph(const GmpeConfig& c, int wpb) {
   return need <= 72 * 1024 ? mode : 0;
 }
 
-// Worlds with N = L = 3 and no obstacles / walls (BASELINE configs 1-3) run on the
+// Worlds with 2 <= N = L <= 10 and no obstacles / walls (BASELINE configs 1-3 among them) run on the
 // lane-per-agent kernel (gmpe_coop.cuh).  GMPE_KERNEL=tile | world | coop overrides the
 // choice (A/B timing, and the tests that keep every mapping pinned to the oracle).
 enum { KERNEL_TILE = 0, KERNEL_WORLD = 1, KERNEL_COOP = 2 };
 static int pick_kernel(const GmpeConfig& c) {
   if (rot_inv(c)) return KERNEL_COOP;  // only the lane-per-agent kernel serves that family (2 <= N = L <= 10)
-  const bool small = c.num_agents == 3 && c.num_landmarks == 3 && c.num_obstacles == 0 && c.num_walls == 0;
+  const bool small = c.num_agents >= COOP_MIN_AGENTS && c.num_agents <= COOP_MAX_AGENTS && c.num_landmarks == c.num_agents &&
+                     c.num_obstacles == 0 && c.num_walls == 0;
   if (!small) return KERNEL_TILE;
   if (const char* t = getenv("GMPE_FORCE_TILE")) if (atoi(t)) return KERNEL_TILE;
   if (const char* k = getenv("GMPE_KERNEL")) {
     if (!strcmp(k, "tile")) return KERNEL_TILE;
-    if (!strcmp(k, "world")) return KERNEL_WORLD;
+    if (!strcmp(k, "world")) return c.num_agents == 3 ? KERNEL_WORLD : KERNEL_COOP;  // thread-per-world exists for N = 3 only
   }
   return KERNEL_COOP;
 }

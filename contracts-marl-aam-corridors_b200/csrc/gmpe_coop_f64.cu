@@ -31,8 +31,8 @@ bool bind_n(int n, const void** fn, size_t* smem) {
 
 bool coop_lookup_f64(int scenario, int n, const void** fn, size_t* smem) {
   switch (scenario) {
-    case GMPE_SCEN_JULY_TUBE: if (n != 3) return false; bind<GMPE_SCEN_JULY_TUBE, 3>(fn, smem); return true;
-    case GMPE_SCEN_NAV_GRAPH: if (n != 3) return false; bind<GMPE_SCEN_NAV_GRAPH, 3>(fn, smem); return true;
+    case GMPE_SCEN_JULY_TUBE: return bind_n<GMPE_SCEN_JULY_TUBE>(n, fn, smem);
+    case GMPE_SCEN_NAV_GRAPH: return bind_n<GMPE_SCEN_NAV_GRAPH>(n, fn, smem);
     case GMPE_SCEN_THREE_PHASE: return bind_n<GMPE_SCEN_THREE_PHASE>(n, fn, smem);
     case GMPE_SCEN_TWO_PHASE: return bind_n<GMPE_SCEN_TWO_PHASE>(n, fn, smem);
     case GMPE_SCEN_CORRIDOR_ROT_INV: return bind_n<GMPE_SCEN_CORRIDOR_ROT_INV>(n, fn, smem);

@@ -1,7 +1,7 @@
 // Lookup of the lane-per-agent kernel instantiations (gmpe_coop.cuh).  They are compiled in
 // their own translation units -- one per precision, built in parallel by build.py -- because
-// every (scenario, N) pair is a separate kernel: N = 3 for the july / navigation scenarios and
-// N = 2 .. 10 for the rot-inv family.
+// every (scenario, N) pair is a separate kernel: N = 2 .. 10 for every scenario (worlds with
+// N == L agents / landmarks and no obstacles or walls).
 #pragma once
 #include <cstddef>
 
@@ -9,5 +9,5 @@ namespace gmpe {
 // false: no instantiation for this (scenario, N); fn / smem_bytes untouched
 bool coop_lookup_f32(int scenario, int num_agents, const void** fn, size_t* smem_bytes);
 bool coop_lookup_f64(int scenario, int num_agents, const void** fn, size_t* smem_bytes);
-constexpr int COOP_ROT_INV_MIN_AGENTS = 2, COOP_ROT_INV_MAX_AGENTS = 10;
+constexpr int COOP_MIN_AGENTS = 2, COOP_MAX_AGENTS = 10;
 }  // namespace gmpe

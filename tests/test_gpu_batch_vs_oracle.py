@@ -22,6 +22,12 @@ CASES = {
     "july_n64": dict(args=dict(scenario_name="nav_metered_one_goal_graph_rotate_tube_july", dynamics_type="air_taxi",
                                num_agents=64, num_landmarks=64, world_size=12, episode_length=5, goal_rew=30,
                                collaborative=False), B=9, T=7),
+    # small worlds of other sizes on the lane-per-agent kernel (Philox placement, force physics, july obs)
+    "july_n5": dict(args=dict(scenario_name="nav_metered_one_goal_graph_rotate_tube_july", dynamics_type="air_taxi",
+                              num_agents=5, num_landmarks=5, world_size=4, episode_length=12, goal_rew=30, collaborative=False),
+                    B=400, T=30),
+    "nav_n6": dict(args=dict(scenario_name="navigation_graph", num_agents=6, num_landmarks=6, world_size=3, episode_length=10),
+                   B=300, T=25),
     "nav_n3": dict(args=dict(scenario_name="navigation_graph", episode_length=10), B=1000, T=25),
     "nav_n3_a9_dones": dict(args=dict(scenario_name="navigation_graph", episode_length=10, total_actions=9,
                                       use_dones=True, collaborative=False, num_obstacles=2), B=500, T=25),
