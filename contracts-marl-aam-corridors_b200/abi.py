@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # error codes
 OK, E_INVALID, E_CUDA, E_NULL = 0, -1, -2, -3
@@ -32,6 +32,9 @@ FLAG_GNN_EDGES = 1 << 4
 FLAG_INFO = 1 << 5
 FLAG_WALL_POINT_QUIRK = 1 << 6
 FLAG_CLASSIC_CONTACT = 1 << 7
+FLAG_FORCE_TILE = 1 << 8
+FORMATION_POINT, FORMATION_LINE, FORMATION_CIRCLE = 0, 1, 2
+FORMATIONS = {"point": FORMATION_POINT, "line": FORMATION_LINE, "circle": FORMATION_CIRCLE}
 
 MAX_AGENTS = 64
 MAX_ENTITIES = 160
@@ -60,6 +63,7 @@ class GmpeConfig(C.Structure):
         ("num_worlds", C.c_int32), ("num_agents", C.c_int32), ("num_landmarks", C.c_int32),
         ("num_obstacles", C.c_int32), ("num_walls", C.c_int32), ("episode_length", C.c_int32),
         ("total_actions", C.c_int32), ("flags", C.c_uint32),
+        ("formation", C.c_int32), ("reserved0", C.c_int32),
         ("seed", C.c_uint64), ("world_offset", C.c_int64),
         ("world_size", C.c_double),
         ("goal_rew", C.c_double), ("collision_rew", C.c_double), ("formation_rew", C.c_double),
@@ -105,7 +109,8 @@ class GmpeStepOut(C.Structure):
 
 
 class GmpeStepInject(C.Structure):
-    _fields_ = [("theta_draw", C.c_void_p), ("reset_state", C.POINTER(GmpeState))]
+    _fields_ = [("theta_draw", C.c_void_p), ("reset_state", C.POINTER(GmpeState)),
+                ("reset_draws", C.c_void_p), ("reset_draws_per_world", C.c_int32), ("reserved0", C.c_int32)]
 
 
 #: every symbol include/gmpe.h declares
@@ -113,6 +118,7 @@ EXPORTED_SYMBOLS = (
     "gmpe_abi_version", "gmpe_create", "gmpe_destroy", "gmpe_last_error", "gmpe_layout",
     "gmpe_reset", "gmpe_step", "gmpe_decode_onehot", "gmpe_launch_count", "gmpe_set_seed",
     "gmpe_kernel_name", "gmpe_step_range", "gmpe_decode_onehot_range", "gmpe_step_host", "gmpe_host_wait",
+    "gmpe_placement_overflows",
 )
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -167,6 +173,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.gmpe_launch_count.restype = C.c_int64
     lib.gmpe_kernel_name.argtypes = [C.c_void_p]
     lib.gmpe_kernel_name.restype = C.c_char_p
+    lib.gmpe_placement_overflows.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
+    lib.gmpe_placement_overflows.restype = C.c_int
     lib.gmpe_set_seed.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
     lib.gmpe_set_seed.restype = C.c_int
     v = lib.gmpe_abi_version()

@@ -88,11 +88,16 @@ def make_struct(cls, arrays: dict):
     return s
 
 
-def make_inject(theta=None, reset_state: dict | None = None):
-    """Returns (GmpeStepInject, keepalive)."""
+def make_inject(theta=None, reset_state: dict | None = None, reset_draws=None):
+    """Returns (GmpeStepInject, keepalive).  ``reset_draws``: float64 (B, K) uniform [0,1) numbers
+    (numpy for the oracle, a device tensor for the engine) a reset consumes instead of Philox."""
     inj = abi.GmpeStepInject()
-    keep = [theta]
+    keep = [theta, reset_draws]
     inj.theta_draw = _ptr(theta)
+    if reset_draws is not None:
+        assert reset_draws.ndim == 2
+        inj.reset_draws = _ptr(reset_draws)
+        inj.reset_draws_per_world = int(reset_draws.shape[1])
     if reset_state is not None:
         rs = make_struct(abi.GmpeState, reset_state)
         keep += [rs, reset_state]

@@ -100,10 +100,16 @@ def num_discrete_actions(args) -> int:
     return int(args.total_actions)
 
 
+#: testing / A-B timing: make_config adds GMPE_FLAG_FORCE_TILE when set (tests/conftest.py's
+#: ``kernel_variant`` fixture flips it so that both kernel mappings stay pinned to the oracle)
+FORCE_TILE_DEFAULT = False
+
+
 def make_config(args, num_worlds: int, *, precision: str = "fp32", seed: int | None = None,
                 world_offset: int = 0, auto_reset: bool = True, env_edges: bool = True,
                 gnn_edges: bool = False, info: bool = True, physics: str | None = None,
-                wall_point_quirk: bool = False, classic_contact: bool = False) -> abi.GmpeConfig:
+                wall_point_quirk: bool = False, classic_contact: bool = False,
+                force_tile: bool | None = None) -> abi.GmpeConfig:
     name = args.scenario_name
     if name in JULY_SCENARIOS:
         scen = abi.SCEN_JULY_TUBE
@@ -125,6 +131,19 @@ def make_config(args, num_worlds: int, *, precision: str = "fp32", seed: int | N
         raise NotImplementedError("the HJ/CBF safety filter (multiagent/safety_filter.py) is out of scope")
     if getattr(args, "num_scripted_agents", 0):
         raise NotImplementedError("scripted agents are out of scope")
+    feat = getattr(args, "graph_feat_type", "relative")
+    if feat != "relative":
+        # july:1612-1616 / _get_entity_feat_global (:1672): 7 global-frame features per node while the
+        # declared node space stays (E, 8) (environment.py:1004); no shipped command or checkpoint uses it
+        raise NotImplementedError(f"graph_feat_type={feat!r}: only 'relative' node features are served "
+                                  "(the reference's 'global' branch, july:1612-1616, is not built)")
+    formation = getattr(args, "formation_type", "point")
+    if formation not in abi.FORMATIONS:
+        # july:492-499: anything else leaves the landmarks where the last episode put them
+        raise NotImplementedError(f"formation_type={formation!r}: the reference places landmarks for "
+                                  f"{tuple(abi.FORMATIONS)} only (july:492-497)")
+    if scen == abi.SCEN_NAV_GRAPH and formation != "point":
+        raise NotImplementedError("navigation_graph places its goals at random (DESIGN.md D1); formation_type must stay 'point'")
     if physics is None:
         physics = "force" if scen == abi.SCEN_NAV_GRAPH else "kinematic"
     c = abi.GmpeConfig()
@@ -158,7 +177,10 @@ def make_config(args, num_worlds: int, *, precision: str = "fp32", seed: int | N
         flags |= abi.FLAG_WALL_POINT_QUIRK
     if classic_contact:
         flags |= abi.FLAG_CLASSIC_CONTACT
+    if FORCE_TILE_DEFAULT if force_tile is None else force_tile:
+        flags |= abi.FLAG_FORCE_TILE
     c.flags = flags
+    c.formation = abi.FORMATIONS[formation]
     c.seed = int(args.seed if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
     c.world_offset = int(world_offset)
     c.world_size = float(args.world_size)
@@ -216,3 +238,12 @@ def validate(c: abi.GmpeConfig) -> None:
         raise ValueError("double_integrator supports total_actions 5 or 9 (environment.py:404-409)")
     if not math.isfinite(c.world_size) or c.world_size <= 0:
         raise ValueError("world_size must be positive")
+    # bounded rejection sampling on the device: refuse what cannot be packed (gmpe_api.cu validate())
+    rot = c.scenario in abi.ROT_INV_SCENARIOS
+    side = 0.9 * c.world_size if c.scenario == abi.SCEN_NAV_GRAPH else (0.6 if rot else 0.4) * c.world_size
+    # tube scenarios stagger the spawn points by 1/5 (july:470) or 1/3 (tp:430) per agent along one axis
+    length = side if c.scenario == abi.SCEN_NAV_GRAPH else side + (N - 1) / (3.0 if rot else 5.0)
+    need = N * math.pi * 0.25 * c.separation_dist ** 2 + O * math.pi * 16.0 * c.entity_size ** 2
+    if need > 0.5 * side * length:
+        raise ValueError("agents cannot be packed: N * pi * (separation_dist / 2)^2 exceeds half of the spawn area "
+                         "(raise world_size)")

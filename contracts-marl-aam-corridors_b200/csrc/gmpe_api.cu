@@ -3,19 +3,85 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 #include <utility>
 #include <algorithm>
 
 #include "gmpe_coop.cuh"
 #include "gmpe_coop_table.h"
-#include "gmpe_small.cuh"
 #include "gmpe_step.cuh"
 
 using namespace gmpe;
+
+// Staging of a pageable action block into page-locked memory (gmpe_step_host) on a few helper
+// threads: a single-threaded memcpy moves ~10 GB/s, which put 0.8 ms of copy in front of a
+// 1.3 ms step for the runner's 7.9 MB float64 one-hot block.  The helpers are created on the
+// first host step that needs staging and sleep on a condition variable in between.
+class StagePool {
+ public:
+  explicit StagePool(int helpers) {
+    for (int t = 0; t < helpers; ++t) th_.emplace_back([this, t] { run(t); });
+  }
+  ~StagePool() {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      quit_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  // dst[0, n) = src[0, n), split over the helpers and the calling thread
+  void copy(char* dst, const char* src, size_t n) {
+    const size_t parts = th_.size() + 1;
+    if (n < (size_t)256 * 1024 || parts == 1) { memcpy(dst, src, n); return; }
+    const size_t chunk = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
+    {
+      std::lock_guard<std::mutex> g(m_);
+      dst_ = dst; src_ = src; n_ = n; chunk_ = chunk;
+      pending_ = (int)th_.size();
+      ++gen_;
+    }
+    cv_.notify_all();
+    if (n > chunk * th_.size()) memcpy(dst + chunk * th_.size(), src + chunk * th_.size(), n - chunk * th_.size());
+    std::unique_lock<std::mutex> g(m_);
+    done_.wait(g, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void run(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      char* d; const char* s; size_t n, c;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return quit_ || gen_ != seen; });
+        if (quit_) return;
+        seen = gen_;
+        d = dst_; s = src_; n = n_; c = chunk_;
+      }
+      const size_t lo = c * (size_t)t;
+      if (lo < n) memcpy(d + lo, s + lo, std::min(c, n - lo));
+      {
+        std::lock_guard<std::mutex> g(m_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  char* dst_ = nullptr;
+  const char* src_ = nullptr;
+  size_t n_ = 0, chunk_ = 0;
+  uint64_t gen_ = 0;
+  int pending_ = 0;
+  bool quit_ = false;
+};
 
 struct gmpe_ctx {
   GmpeConfig cfg;
@@ -27,15 +93,21 @@ struct gmpe_ctx {
   int grid;
   size_t smem_bytes;
   int stage_graph;
-  int small;  // KERNEL_TILE (gmpe_step.cuh) / KERNEL_WORLD (gmpe_small.cuh) / KERNEL_COOP (gmpe_coop.cuh)
+  int small;  // KERNEL_TILE (gmpe_step.cuh) / KERNEL_COOP (gmpe_coop.cuh)
   const void* fn;
   int64_t resident;  // CTAs of the step kernel that fit on the device at once
-  void* act_tab;  // device copy of the _set_action table (Real [32][2]); the only memory the library owns
+  void* act_tab;  // device copy of the _set_action table (Real [32][2]) followed by the placement-overflow counter
+                  // (one 64-bit word at byte ACT_TAB_BYTES): the only device memory the library owns
   int64_t launches;
   std::string err;
   // gmpe_step_host: copy streams and per-slice events, created on first use
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev;
+  // tail of the last host step's device->host copies: a later launch on ANY stream waits for it
+  // before it overwrites the device outputs those copies are reading
+  cudaEvent_t ev_tail = nullptr;
+  bool tail_pending = false;
+  StagePool* pool = nullptr;
 };
 
 static thread_local std::string g_create_err;
@@ -52,6 +124,19 @@ static int obs_dim_of(const GmpeConfig& c) {
   return c.scenario == GMPE_SCEN_JULY_TUBE ? 19 : (c.scenario == GMPE_SCEN_CORRIDOR_ROT_INV ? 13 : (rot_inv(c) ? 15 : 6));
 }
 static int node_dim_of(const GmpeConfig& c) { return rot_inv(c) ? 7 : 8; }
+
+enum { ACT_TAB_BYTES = 512 };  // Real [32][2] at fp64; the overflow counter sits right behind it
+
+// Tuning knobs read from the environment exist only in GMPE_EXPERIMENTS builds (tools/sweep.py,
+// tools/ab.py): the product library's behaviour depends on its arguments alone.
+static const char* tuning_env(const char* name) {
+#ifdef GMPE_EXPERIMENTS
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
 
 static const char* validate(const GmpeConfig& c) {
   if (c.scenario != GMPE_SCEN_JULY_TUBE && c.scenario != GMPE_SCEN_NAV_GRAPH && !rot_inv(c)) return "unknown scenario";
@@ -73,6 +158,20 @@ static const char* validate(const GmpeConfig& c) {
   if (c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR && c.total_actions != 25) return "unicycle / air_taxi use the 25 motion primitives";
   if (c.episode_length < 1) return "episode_length must be >= 1";
   if (!(c.world_size > 0)) return "world_size must be positive";
+  if (c.formation < GMPE_FORMATION_POINT || c.formation > GMPE_FORMATION_CIRCLE) return "unknown formation";
+  if (c.reserved0 != 0) return "GmpeConfig.reserved0 must be 0";
+  {
+    // Spawn placement is rejection sampling on the device (bounded, see gmpe_placement_overflows):
+    // refuse what cannot be packed.  Agents keep separation_dist between each other inside the
+    // spawn box -- 0.9 * world_size square (navigation), jitter box of side 2 * 0.2 (july) or
+    // 2 * 0.3 (rot-inv) * world_size around spawn points staggered by 1/5 (july:470) or 1/3 (tp:430)
+    // per agent along one axis.
+    const double side = c.scenario == GMPE_SCEN_NAV_GRAPH ? 0.9 * c.world_size : (rot_inv(c) ? 0.6 : 0.4) * c.world_size;
+    const double length = c.scenario == GMPE_SCEN_NAV_GRAPH ? side : side + (c.num_agents - 1) / (rot_inv(c) ? 3.0 : 5.0);
+    const double need = c.num_agents * 3.141592653589793 * 0.25 * c.separation_dist * c.separation_dist +
+                        c.num_obstacles * 3.141592653589793 * 16.0 * c.entity_size * c.entity_size;
+    if (need > 0.5 * side * length) return "agents cannot be packed: N * pi * (separation_dist / 2)^2 exceeds half of the spawn area (raise world_size)";
+  }
   return nullptr;
 }
 
@@ -117,19 +216,15 @@ static int pick_stage_graph(const GmpeConfig& c, int wpb) {
 }
 
 // Worlds with 2 <= N = L <= 10 and no obstacles / walls (BASELINE configs 1-3 among them) run on the
-// lane-per-agent kernel (gmpe_coop.cuh).  GMPE_KERNEL=tile | world | coop overrides the
-// choice (A/B timing, and the tests that keep every mapping pinned to the oracle).
-enum { KERNEL_TILE = 0, KERNEL_WORLD = 1, KERNEL_COOP = 2 };
+// lane-per-agent kernel (gmpe_coop.cuh).  GMPE_FLAG_FORCE_TILE in the configuration overrides
+// the choice (A/B timing, and the tests that keep both mappings pinned to the oracle).
+enum { KERNEL_TILE = 0, KERNEL_COOP = 2 };
 static int pick_kernel(const GmpeConfig& c) {
   if (rot_inv(c)) return KERNEL_COOP;  // only the lane-per-agent kernel serves that family (2 <= N = L <= 10)
   const bool small = c.num_agents >= COOP_MIN_AGENTS && c.num_agents <= COOP_MAX_AGENTS && c.num_landmarks == c.num_agents &&
                      c.num_obstacles == 0 && c.num_walls == 0;
   if (!small) return KERNEL_TILE;
-  if (const char* t = getenv("GMPE_FORCE_TILE")) if (atoi(t)) return KERNEL_TILE;
-  if (const char* k = getenv("GMPE_KERNEL")) {
-    if (!strcmp(k, "tile")) return KERNEL_TILE;
-    if (!strcmp(k, "world")) return c.num_agents == 3 ? KERNEL_WORLD : KERNEL_COOP;  // thread-per-world exists for N = 3 only
-  }
+  if (c.flags & GMPE_FLAG_FORCE_TILE) return KERNEL_TILE;
   return KERNEL_COOP;
 }
 
@@ -139,15 +234,15 @@ static int pick_kernel(const GmpeConfig& c) {
 static int grid_for(const gmpe_ctx* h, int64_t units) {
   const int64_t g = h->resident;
   bool persistent = true;
-  if (const char* t = getenv("GMPE_PERSISTENT")) persistent = atoi(t) != 0;  // tuning knob (tools/ab.py)
+  if (const char* t = tuning_env("GMPE_PERSISTENT")) persistent = atoi(t) != 0;  // tuning knob (tools/ab.py)
   if (units <= g || !persistent) return (int)units;
-  if (const char* t = getenv("GMPE_GRID")) { const int v = atoi(t); if (v > 0 && v <= units) return v; }  // tuning knob
+  if (const char* t = tuning_env("GMPE_GRID")) { const int v = atoi(t); if (v > 0 && v <= units) return v; }  // tuning knob
   // lane-per-agent kernel: every SM gets the same number of CTAs, the partial last round is
   // spread over all of them at warp granularity (gmpe_coop.cuh); 30.8 -> 30.1 us at 65,536
   // navigation worlds, 60.9 -> 59.8 us at 131,072 july worlds against the rounded-down grid below
   if (h->small == KERNEL_COOP && GMPE_COOP_TRANSPOSE_TAIL) return (int)g;
   const int64_t rounds = (units + g - 1) / g;
-  if (const char* t = getenv("GMPE_BALANCED")) if (!atoi(t)) return (int)g;
+  if (const char* t = tuning_env("GMPE_BALANCED")) if (!atoi(t)) return (int)g;
   return (int)((units + rounds - 1) / rounds);
 }
 
@@ -246,7 +341,6 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
   cudaSetDevice(device);
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   const bool f64 = cfg->precision == GMPE_F64;
-  const bool july = cfg->scenario == GMPE_SCEN_JULY_TUBE;
   h->small = pick_kernel(h->cfg);
   int units = 0;  // CTAs needed to cover the batch once
   if (h->small == KERNEL_COOP) {
@@ -263,22 +357,9 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
       delete h;
       return code;
     }
-  } else if (h->small == KERNEL_WORLD) {
-    // one thread per world, warps are independent: see gmpe_small.cuh
-    h->threads = 32 * GMPE_SMALL_WARPS;
-    h->wpb = h->threads;
-    h->num_tiles = (cfg->num_worlds + h->wpb - 1) / h->wpb;
-    h->stage_graph = 0;
-    if (f64) {
-      h->fn = july ? (const void*)gmpe_step_small_kernel<double, GMPE_SCEN_JULY_TUBE, 3> : (const void*)gmpe_step_small_kernel<double, GMPE_SCEN_NAV_GRAPH, 3>;
-      h->smem_bytes = GMPE_SMALL_WARPS * (july ? SmallTraits<double, GMPE_SCEN_JULY_TUBE, 3>::SLAB_BYTES : SmallTraits<double, GMPE_SCEN_NAV_GRAPH, 3>::SLAB_BYTES);
-    } else {
-      h->fn = july ? (const void*)gmpe_step_small_kernel<float, GMPE_SCEN_JULY_TUBE, 3> : (const void*)gmpe_step_small_kernel<float, GMPE_SCEN_NAV_GRAPH, 3>;
-      h->smem_bytes = GMPE_SMALL_WARPS * (july ? SmallTraits<float, GMPE_SCEN_JULY_TUBE, 3>::SLAB_BYTES : SmallTraits<float, GMPE_SCEN_NAV_GRAPH, 3>::SLAB_BYTES);
-    }
   } else {
     h->threads = GMPE_LB_THREADS;
-    if (const char* t = getenv("GMPE_THREADS")) {  // tuning knob (tools/sweep.py); must not exceed the launch bound
+    if (const char* t = tuning_env("GMPE_THREADS")) {  // tuning knob (tools/sweep.py); must not exceed the launch bound
       int v = atoi(t);
       if (v >= 32 && v <= GMPE_LB_THREADS && v % 32 == 0) h->threads = v;
     }
@@ -288,7 +369,8 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
     h->fn = f64 ? (const void*)gmpe_step_kernel<double> : (const void*)gmpe_step_kernel<float>;
     // fp32 instantiations with compile-time entity counts for the BASELINE shapes
     const GmpeConfig& q = h->cfg;
-    const bool generic = getenv("GMPE_GENERIC_SHAPE") && atoi(getenv("GMPE_GENERIC_SHAPE"));
+    const char* gs = tuning_env("GMPE_GENERIC_SHAPE");
+    const bool generic = gs && atoi(gs);
     if (!f64 && !generic) {
       if (q.num_agents == 16 && q.num_landmarks == 16 && q.num_obstacles == 8 && q.num_walls == 4 &&
           q.scenario == GMPE_SCEN_NAV_GRAPH && q.dynamics == GMPE_DYN_DOUBLE_INTEGRATOR)
@@ -330,7 +412,9 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
       tf[2 * a] = f0; tf[2 * a + 1] = f1;
     }
     const size_t nbytes = f64 ? sizeof(td) : sizeof(tf);
-    e = cudaMalloc(&h->act_tab, nbytes);
+    static_assert(sizeof(td) <= ACT_TAB_BYTES, "action table");
+    e = cudaMalloc(&h->act_tab, ACT_TAB_BYTES + 8);
+    if (e == cudaSuccess) e = cudaMemset(h->act_tab, 0, ACT_TAB_BYTES + 8);
     if (e == cudaSuccess) e = cudaMemcpy(h->act_tab, f64 ? (const void*)td : (const void*)tf, nbytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       std::string m = std::string("gmpe_create: ") + cudaGetErrorString(e);
@@ -356,7 +440,9 @@ int gmpe_destroy(gmpe_handle h) {
     cudaGetDevice(&prev);
     cudaSetDevice(h->device);
     if (h->act_tab) cudaFree(h->act_tab);
+    delete h->pool;
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    if (h->ev_tail) cudaEventDestroy(h->ev_tail);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     cudaSetDevice(prev);
@@ -371,7 +457,23 @@ int64_t gmpe_launch_count(gmpe_handle h) { return h ? h->launches : 0; }
 
 const char* gmpe_kernel_name(gmpe_handle h) {
   if (!h) return "";
-  return h->small == KERNEL_COOP ? "gmpe_step_coop_kernel" : (h->small == KERNEL_WORLD ? "gmpe_step_small_kernel" : "gmpe_step_kernel");
+  return h->small == KERNEL_COOP ? "gmpe_step_coop_kernel" : "gmpe_step_kernel";
+}
+
+int gmpe_placement_overflows(gmpe_handle h, int64_t* count, int clear) {
+  if (!h || !count) return GMPE_E_NULL;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  unsigned long long v = 0;
+  void* cnt = (char*)h->act_tab + ACT_TAB_BYTES;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(&v, cnt, 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && clear) e = cudaMemset(cnt, 0, 8);
+  if (prev != h->device) cudaSetDevice(prev);
+  if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("gmpe_placement_overflows: ") + cudaGetErrorString(e));
+  *count = (int64_t)v;
+  return GMPE_OK;
 }
 
 int gmpe_set_seed(gmpe_handle h, uint64_t seed, int64_t world_offset) {
@@ -382,7 +484,8 @@ int gmpe_set_seed(gmpe_handle h, uint64_t seed, int64_t world_offset) {
 }
 
 static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* act, const uint8_t* mask,
-                  const GmpeStepInject* inj, const GmpeStepOut* out, void* stream, int64_t b0 = 0, int64_t count = -1) {
+                  const GmpeStepInject* inj, const GmpeStepOut* out, void* stream, int64_t b0 = 0, int64_t count = -1,
+                  bool in_host_step = false) {
   const GmpeConfig& c = h->cfg;
   if (count < 0) count = c.num_worlds;
   if (b0 < 0 || count < 1 || b0 + count > c.num_worlds) return fail(h, GMPE_E_INVALID, "world range outside [0, num_worlds)");
@@ -408,6 +511,11 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   p.theta = inj ? inj->theta_draw : nullptr;
   p.has_rst = (inj && inj->reset_state) ? 1 : 0;
   if (p.has_rst) p.rst = *inj->reset_state;
+  if (inj && inj->reset_draws && inj->reset_draws_per_world > 0) {
+    p.reset_draws = inj->reset_draws;
+    p.reset_draws_n = inj->reset_draws_per_world;
+  }
+  p.overflow_cnt = reinterpret_cast<unsigned long long*>((char*)h->act_tab + ACT_TAB_BYTES);
   p.mode = mode;
   p.wpb = h->wpb;
   p.num_tiles = h->num_tiles;
@@ -420,6 +528,7 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
     shift(p.act, b0 * c.num_agents);
     shift(p.env_mask, b0);
     shift_bytes(p.theta, b0 * c.num_agents * R);
+    shift(p.reset_draws, b0 * p.reset_draws_n);
     p.c.num_worlds = (int32_t)count;
     p.c.world_offset += b0;  // Philox streams are keyed by the global world id
     p.num_tiles = (int)((count + h->wpb - 1) / h->wpb);
@@ -431,9 +540,7 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   p.F = obs_dim_of(c);
   p.dN = FastDiv::make(N); p.dE = FastDiv::make(p.E); p.dL = FastDiv::make(L); p.dO = FastDiv::make(O);
   p.dW = FastDiv::make(W); p.dF = FastDiv::make(p.F); p.d16 = FastDiv::make(16);
-#ifdef GMPE_EXPERIMENTS
-  if (const char* t = getenv("GMPE_XMODE")) p.xmode = atoi(t);
-#endif
+  if (const char* t = tuning_env("GMPE_XMODE")) p.xmode = atoi(t);
   p.act_tab = h->act_tab;
   p.dE2 = FastDiv::make(p.E * 2); p.dNE2 = FastDiv::make(N * p.E * 2); p.dEE = FastDiv::make(p.E * p.E);
   int prev = 0;
@@ -441,7 +548,10 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   if (prev != h->device) cudaSetDevice(h->device);
   cudaStream_t s = (cudaStream_t)stream;
   void* kargs[1] = {(void*)&p};
-  cudaError_t e = cudaLaunchKernel(h->fn, dim3(grid), dim3(h->threads), kargs, h->smem_bytes, s);
+  cudaError_t e = cudaSuccess;
+  // the copies of an uncollected host step still read the device outputs this launch rewrites
+  if (h->tail_pending && !in_host_step) e = cudaStreamWaitEvent(s, h->ev_tail, 0);
+  if (e == cudaSuccess) e = cudaLaunchKernel(h->fn, dim3(grid), dim3(h->threads), kargs, h->smem_bytes, s);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (prev != h->device) cudaSetDevice(prev);
   if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e));
@@ -546,7 +656,14 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
     e = cudaEventCreateWithFlags(&v, cudaEventDisableTiming);
     if (e == cudaSuccess) h->ev.push_back(v);
   }
+  if (e == cudaSuccess && !h->ev_tail) e = cudaEventCreateWithFlags(&h->ev_tail, cudaEventDisableTiming);
+  if (actions_pinned != actions_host && !h->pool) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    h->pool = new (std::nothrow) StagePool(hw >= 8 ? 3 : (hw >= 4 ? 1 : 0));
+  }
   int rc = GMPE_OK;
+  // a previous host step whose results were never collected: its copies read the device outputs
+  if (e == cudaSuccess && h->tail_pending) e = cudaStreamWaitEvent(main_s, h->ev_tail, 0);
   if (e == cudaSuccess) {  // the copy-in stream starts behind whatever the caller has queued on its stream
     e = cudaEventRecord(h->ev[2 * sl.size()], main_s);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_in, h->ev[2 * sl.size()], 0);
@@ -554,14 +671,17 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
   for (size_t k = 0; k < sl.size() && e == cudaSuccess && rc == GMPE_OK; ++k) {
     const int64_t b0 = sl[k].first, cnt = sl[k].second;
     const int64_t off = b0 * act_bpw, nb = cnt * act_bpw;
-    if (actions_pinned != actions_host) memcpy((char*)actions_pinned + off, (const char*)actions_host + off, (size_t)nb);
+    if (actions_pinned != actions_host) {
+      if (h->pool) h->pool->copy((char*)actions_pinned + off, (const char*)actions_host + off, (size_t)nb);
+      else memcpy((char*)actions_pinned + off, (const char*)actions_host + off, (size_t)nb);
+    }
     e = cudaMemcpyAsync((char*)actions_dev + off, (const char*)actions_pinned + off, (size_t)nb, cudaMemcpyHostToDevice, h->s_in);
     if (e == cudaSuccess) e = cudaEventRecord(h->ev[2 * k], h->s_in);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(main_s, h->ev[2 * k], 0);
     if (e != cudaSuccess) break;
     const int32_t* idx = action_kind == 0 ? (const int32_t*)actions_dev : idx_dev;
     if (action_kind != 0) rc = gmpe_decode_onehot_range(h, actions_dev, action_kind, idx_dev, b0, cnt, cuda_stream);
-    if (rc == GMPE_OK) rc = launch(h, MODE_STEP, st, idx, nullptr, nullptr, dev_out, cuda_stream, b0, cnt);
+    if (rc == GMPE_OK) rc = launch(h, MODE_STEP, st, idx, nullptr, nullptr, dev_out, cuda_stream, b0, cnt, true);
     if (rc != GMPE_OK) break;
     cudaSetDevice(h->device);  // (the calls above restore the caller's device)
     e = cudaEventRecord(h->ev[2 * k + 1], main_s);
@@ -570,6 +690,10 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
       if (dptr[f] && hptr[f])
         e = cudaMemcpyAsync((char*)hptr[f] + b0 * bpw[f], (const char*)dptr[f] + b0 * bpw[f], (size_t)(cnt * bpw[f]),
                             cudaMemcpyDeviceToHost, h->s_out);
+  }
+  if (e == cudaSuccess && rc == GMPE_OK) {
+    e = cudaEventRecord(h->ev_tail, h->s_out);
+    h->tail_pending = e == cudaSuccess;
   }
   if (prev != h->device) cudaSetDevice(prev);
   if (rc != GMPE_OK) return rc;
@@ -582,6 +706,7 @@ int gmpe_host_wait(gmpe_handle h) {
   if (!h->s_out) return GMPE_OK;
   cudaError_t e = cudaStreamSynchronize(h->s_out);
   if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("gmpe_host_wait: ") + cudaGetErrorString(e));
+  h->tail_pending = false;
   return GMPE_OK;
 }
 

@@ -17,11 +17,11 @@
 // on an agent's own state is computed first and exchanged, then agent i reads the
 // post-reward value of agents < i and the pre-reward value of agents > i.
 //
-// Compared with the thread-per-world kernel (gmpe_small.cuh) this gives 3.2x the warps for
-// the same batch and a third of the straight-line code per warp -- that kernel was bound by
-// latency (13.8 warps / SM at 65,536 worlds) and instruction fetch, not by bandwidth.
+// (An earlier thread-per-world mapping -- a whole world in one lane's registers -- had a third
+// of the warps for the same batch and three times the straight-line code per warp: it was bound
+// by latency, 13.8 warps / SM at 65,536 worlds, and instruction fetch, and has been removed.)
 #pragma once
-#include "gmpe_small.cuh"
+#include "gmpe_place.cuh"
 
 namespace gmpe {
 
@@ -602,7 +602,10 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         s = ((const V4*)p.rst.agent_state)[ga];
         aux.y = ((const V2*)p.rst.agent_aux)[ga].y;
       } else {
-        const Placed<Real, N> pl = place_small<Real, SCEN, N>(c, c.world_offset + b, (uint32_t)wep);
+        const DrawSrc ds{c.seed, c.world_offset + b, (uint32_t)wep,
+                         p.reset_draws ? p.reset_draws + (size_t)b * p.reset_draws_n : nullptr, (uint32_t)p.reset_draws_n};
+        const Placed<Real, N> pl = place_small<Real, SCEN, N>(c, ds);
+        if (pl.overflow && i == 0 && p.overflow_cnt) atomicAdd(p.overflow_cnt, 1ull);
         if (tube) {
 #pragma unroll
           for (int q = 0; q < 12; ++q) wf[q] = pl.wf[q];

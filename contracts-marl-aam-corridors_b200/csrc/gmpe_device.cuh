@@ -72,6 +72,55 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, int64_t world, u
   return lo + (hi - lo) * philox_uniform01(seed, world, ep, idx);
 }
 
+// Source of the uniform draws of one world's reset: Philox, or -- teacher forcing for reset
+// parity against the reference's own np.random stream -- the caller's buffer of uniform [0, 1)
+// doubles (GmpeStepInject.reset_draws), consumed in the order reset_world calls np.random
+// (july:368, :530, :467, core.py:328); NaN entries and indices past the buffer fall back to Philox.
+struct DrawSrc {
+  uint64_t seed;
+  int64_t gw;      // global world id
+  uint32_t ep;     // episode counter
+  const double* inj;  // this world's injected draws or nullptr
+  uint32_t inj_n;
+  __device__ __forceinline__ double u01(uint32_t idx) const {
+    if (inj && idx < inj_n) {
+      const double u = inj[idx];
+      if (u == u) return u;
+    }
+    return philox_uniform01(seed, gw, ep, idx);
+  }
+  __device__ __forceinline__ double uniform(uint32_t idx, double lo, double hi) const { return lo + (hi - lo) * u01(idx); }  // np.random.uniform
+};
+
+// Rejection sampling of spawn positions is bounded: the reference loops until a draw fits
+// (july:452-486) and can be interrupted; a kernel cannot.  After this many rejected draws the
+// last one is kept and the handle's overflow counter is raised (gmpe_placement_overflows).
+#ifndef GMPE_PLACE_MAX_ATTEMPTS
+#define GMPE_PLACE_MAX_ATTEMPTS 1024
+#endif
+
+// Landmark l of L for GmpeConfig.formation (july:492-497): 'point' = set_landmarks_in_point
+// (utils.py:165-193: (0, -ws/3) rotated by the tube angle, from the tube exit); 'line' =
+// set_landmarks_in_line (utils.py:77-131) from (-ws/2, -ws/2) to (ws/2, -ws/2) with np.linspace's
+// arithmetic for a vector whose y-step is zero ((l / div) * delta + start, last = stop);
+// 'circle' = set_landmarks_in_circle (utils.py:231-262), centre (0, exit_y + ws/5), radius ws/3.
+__host__ __device__ __forceinline__ void formation_landmark(const GmpeConfig& c, int l, int L, double ext0, double ext1, double sa,
+                                                            double ca, double& lx, double& ly) {
+  const double ws = c.world_size;
+  if (c.formation == GMPE_FORMATION_LINE) {
+    const double start = -ws / 2, stop = ws / 2;
+    lx = (L > 1 && l == L - 1) ? stop : (L > 1 ? ((double)l / (double)(L - 1)) * (stop - start) + start : start);
+    ly = -ws / 2;
+  } else if (c.formation == GMPE_FORMATION_CIRCLE) {
+    const double ang = (double)l * (2 * 3.141592653589793 / (double)L);
+    lx = 0.0 + (ws / 3) * cos(ang);
+    ly = (ext1 + ws / 5) + (ws / 3) * sin(ang);
+  } else {
+    lx = ext0 + sa * (-ws / 3);
+    ly = ext1 + ca * (-ws / 3);
+  }
+}
+
 // ---- scalar math --------------------------------------------------------------------
 __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
 // fp32 production arithmetic.  IEEE sqrtf and the IEEE fp32 quotient cost 10-12 instructions

@@ -45,6 +45,9 @@ struct KParams {
   FastDiv dN, dE, dL, dO, dW, dF, d16, dE2, dNE2, dEE;
   int xmode;       // GMPE_EXPERIMENTS builds only (tools/ab.py): 1 = skip physics/reward, 2 = skip emission
   const void* act_tab;  // Real [32][2]: _set_action table (decode_action evaluated on the host), device memory owned by the handle
+  const double* reset_draws;  // GmpeStepInject.reset_draws (already re-based on the launch's first world) or nullptr
+  int reset_draws_n;          // ... doubles per world
+  unsigned long long* overflow_cnt;  // worlds whose placement gave up a rejection loop (device counter owned by the handle)
 };
 
 // ---- shared memory carve-up --------------------------------------------------------
@@ -421,17 +424,17 @@ __device__ __noinline__ void place_world(const KParams& p, const Smem<Real>& sm,
   typename RT<Real>::V4* nst = sm.nst + lw * N;
   Real* wf = sm.wf + lw * GMPE_WORLD_F;
   Real* wl = sm.wl + lw * W * GMPE_WALL_F;
-  const uint64_t seed = c.seed;
-  const int64_t gw = c.world_offset + b;
-  const uint32_t ep = (uint32_t)sm.wep[lw];
+  const DrawSrc ds{c.seed, c.world_offset + b, (uint32_t)sm.wep[lw],
+                   p.reset_draws ? p.reset_draws + (size_t)b * p.reset_draws_n : nullptr, (uint32_t)p.reset_draws_n};
   uint32_t idx = 0;
+  bool overflow = false;
   const double ws = c.world_size;
   const bool heading = c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR;
   const Real sep = Real(c.separation_dist);
   if (c.scenario == GMPE_SCEN_JULY_TUBE) {
-    (void)philox_uniform01(seed, gw, ep, idx++);  // wall_length draw (july:368), value unused
+    (void)ds.u01(idx++);  // wall_length draw (july:368), value unused
     double width = fmax(3 * c.entity_size * 2.5, ws * 0.15);
-    double angle = philox_uniform(seed, gw, ep, idx++, -1.5707963267948966, 1.5707963267948966);
+    double angle = ds.uniform(idx++, -1.5707963267948966, 1.5707963267948966);
     double tl = ws * 0.8, ca, sa;
     sincos(angle, &sa, &ca);
     double ent0 = sa * (tl / 4), ent1 = ca * (tl / 4), ext0 = sa * (-tl / 4), ext1 = ca * (-tl / 4);
@@ -443,22 +446,28 @@ __device__ __noinline__ void place_world(const KParams& p, const Smem<Real>& sm,
     wf[GMPE_WF_N_X] = Real((float)(-e1)); wf[GMPE_WF_N_Y] = Real((float)e0);
     wf[GMPE_WF_L] = Real(Lh); wf[GMPE_WF_HALF_W] = Real(width * 0.5);
     wf[GMPE_WF_WIDTH] = Real(width); wf[GMPE_WF_ANGLE] = Real(angle);
-    int k = 0;
+    int k = 0, tries = 0;
     while (k < N) {  // july:452-486
-      double jx = 0.2 * philox_uniform(seed, gw, ep, idx, -ws, ws);
-      double jy = 0.2 * philox_uniform(seed, gw, ep, idx + 1, -ws, ws);
+      double jx = 0.2 * ds.uniform(idx, -ws, ws);
+      double jy = 0.2 * ds.uniform(idx + 1, -ws, ws);
       idx += 2;
       double d = (ws + k) / 5;
       Real px = Real(ent0 + d * sa + jx), py = Real(ent1 + d * ca + jy);
       bool bad = obstacle_collision<Real>(c, pos_w, wl, N, L, O, W, px, py);
       for (int a = 0; a < k && !bad; ++a) bad = norm2(nst[a].x - px, nst[a].y - py) < sep;
-      if (bad) continue;
+      if (bad && ++tries < GMPE_PLACE_MAX_ATTEMPTS) continue;
+      overflow = overflow || bad;  // bounded rejection: keep the last draw (gmpe_placement_overflows)
+      tries = 0;
       Real th = Real(0), v = Real(0);
-      if (heading) { th = wrap_heading(Real(philox_uniform(seed, gw, ep, idx++, 0.0, 6.283185307179586))); v = Real(c.v_min); }
+      if (heading) { th = wrap_heading(Real(ds.uniform(idx++, 0.0, 6.283185307179586))); v = Real(c.v_min); }
       nst[k] = RT<Real>::mk4(px, py, th, v);
       ++k;
     }
-    for (int l = 0; l < L; ++l) pos_w[N + l] = RT<Real>::mk2(Real(ext0 + sa * (-ws / 3)), Real(ext1 + ca * (-ws / 3)));
+    for (int l = 0; l < L; ++l) {
+      double lx, ly;
+      formation_landmark(c, l, L, ext0, ext1, sa, ca, lx, ly);
+      pos_w[N + l] = RT<Real>::mk2(Real(lx), Real(ly));
+    }
   } else {
     const double h = ws / 2;
     for (int q = 0; q < W; ++q) {  // boundary box: H top, H bottom, V right, V left
@@ -470,34 +479,38 @@ __device__ __noinline__ void place_world(const KParams& p, const Smem<Real>& sm,
       pos_w[N + L + O + q] = w[0] == Real(0) ? RT<Real>::mk2(mid, w[1]) : RT<Real>::mk2(w[1], mid);
     }
     for (int o = 0; o < O; ++o) {
-      pos_w[N + L + o] = RT<Real>::mk2(Real(0.9 * philox_uniform(seed, gw, ep, idx, -h, h)),
-                                       Real(0.9 * philox_uniform(seed, gw, ep, idx + 1, -h, h)));
+      pos_w[N + L + o] = RT<Real>::mk2(Real(0.9 * ds.uniform(idx, -h, h)), Real(0.9 * ds.uniform(idx + 1, -h, h)));
       idx += 2;
     }
-    int k = 0;
+    int k = 0, tries = 0;
     while (k < N) {
-      Real px = Real(0.9 * philox_uniform(seed, gw, ep, idx, -h, h)), py = Real(0.9 * philox_uniform(seed, gw, ep, idx + 1, -h, h));
+      Real px = Real(0.9 * ds.uniform(idx, -h, h)), py = Real(0.9 * ds.uniform(idx + 1, -h, h));
       idx += 2;
       bool bad = obstacle_collision<Real>(c, pos_w, wl, N, L, O, W, px, py);
       for (int a = 0; a < k && !bad; ++a) bad = norm2(nst[a].x - px, nst[a].y - py) < sep;
-      if (bad) continue;
+      if (bad && ++tries < GMPE_PLACE_MAX_ATTEMPTS) continue;
+      overflow = overflow || bad;
+      tries = 0;
       Real th = Real(0), v = Real(0);
-      if (heading) { th = wrap_heading(Real(philox_uniform(seed, gw, ep, idx++, 0.0, 6.283185307179586))); v = Real(c.v_min); }
+      if (heading) { th = wrap_heading(Real(ds.uniform(idx++, 0.0, 6.283185307179586))); v = Real(c.v_min); }
       nst[k] = RT<Real>::mk4(px, py, th, v);
       ++k;
     }
     const Real lmin = Real(1.2 * (2 * c.entity_size));  // is_landmark_collision july:916-925
-    k = 0;
+    k = 0; tries = 0;
     while (k < L) {
-      Real px = Real(0.9 * philox_uniform(seed, gw, ep, idx, -h, h)), py = Real(0.9 * philox_uniform(seed, gw, ep, idx + 1, -h, h));
+      Real px = Real(0.9 * ds.uniform(idx, -h, h)), py = Real(0.9 * ds.uniform(idx + 1, -h, h));
       idx += 2;
       bool bad = obstacle_collision<Real>(c, pos_w, wl, N, L, O, W, px, py);
       for (int a = 0; a < k && !bad; ++a) bad = norm2(pos_w[N + a].x - px, pos_w[N + a].y - py) < lmin;
-      if (bad) continue;
+      if (bad && ++tries < GMPE_PLACE_MAX_ATTEMPTS) continue;
+      overflow = overflow || bad;
+      tries = 0;
       pos_w[N + k] = RT<Real>::mk2(px, py);
       ++k;
     }
   }
+  if (overflow && p.overflow_cnt) atomicAdd(p.overflow_cnt, 1ull);
 }
 
 // -1 / 0 padding of one world's fixed-capacity edge buffers behind its last edge, by one warp:

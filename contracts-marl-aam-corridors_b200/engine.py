@@ -97,8 +97,15 @@ class BatchedGraphMPE:
         """Which step kernel gmpe_create picked for this configuration."""
         return self.lib.gmpe_kernel_name(self._h).decode()
 
-    def _inject(self, theta_draw, reset_state):
-        if theta_draw is None and reset_state is None:
+    @property
+    def placement_overflows(self) -> int:
+        """Worlds whose spawn placement gave up a rejection loop so far (synchronises the device)."""
+        n = C.c_int64(0)
+        self._check(self.lib.gmpe_placement_overflows(self._h, C.byref(n), 0), "gmpe_placement_overflows")
+        return int(n.value)
+
+    def _inject(self, theta_draw, reset_state, reset_draws=None):
+        if theta_draw is None and reset_state is None and reset_draws is None:
             return self._null_inject, None
         if theta_draw is not None:
             theta_draw = torch.as_tensor(theta_draw, dtype=self.real, device=self.device).contiguous()
@@ -108,12 +115,18 @@ class BatchedGraphMPE:
                 t = torch.as_tensor(v, device=self.device)
                 rs[k] = t.to(self.real if t.is_floating_point() else t.dtype).contiguous()
             reset_state = rs
-        return buffers.make_inject(theta_draw, reset_state)
+        if reset_draws is not None:
+            reset_draws = torch.as_tensor(reset_draws, dtype=torch.float64, device=self.device).contiguous()
+            if reset_draws.ndim != 2 or reset_draws.shape[0] != self.B:
+                raise ValueError(f"reset_draws must have shape ({self.B}, K)")
+        return buffers.make_inject(theta_draw, reset_state, reset_draws)
 
     # -- hot path ---------------------------------------------------------------------
-    def reset(self, env_mask=None, reset_state: dict | None = None, out_struct=None) -> dict:
-        """MultiAgentGraphEnv.reset for every masked world (environment.py:1066-1081)."""
-        inj, keep = self._inject(None, reset_state)
+    def reset(self, env_mask=None, reset_state: dict | None = None, out_struct=None, reset_draws=None) -> dict:
+        """MultiAgentGraphEnv.reset for every masked world (environment.py:1066-1081).
+        ``reset_draws``: float64 (B, K) uniform [0,1) numbers consumed instead of the Philox stream
+        (the reference's own np.random stream in the reset-parity tests)."""
+        inj, keep = self._inject(None, reset_state, reset_draws)
         m = None
         if env_mask is not None:
             m = torch.as_tensor(env_mask, device=self.device).to(torch.uint8).contiguous()

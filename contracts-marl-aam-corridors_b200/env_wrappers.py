@@ -209,9 +209,13 @@ class _BatchedVecEnv(ShareVecEnv):
         # copies run on their own stream while slice k+1's host->device copy and kernel proceed.
         if pipeline_chunks is None:
             pipeline_chunks = 4 if (output == "numpy" and B >= 8192) else 1
-            if os.environ.get("GMPE_PIPELINE_CHUNKS"):  # tuning knob
-                pipeline_chunks = int(os.environ["GMPE_PIPELINE_CHUNKS"])
-        self._chunks = max(1, int(pipeline_chunks))
+        # device-resident outputs have nothing to copy back: one launch, and no host copies in
+        # flight that a later launch could overwrite
+        self._chunks = max(1, int(pipeline_chunks)) if output == "numpy" else 1
+        #: recorded behind every non-blocking upload from a pinned action block; the block is not
+        #: rewritten before the copy has executed (with output="torch" nothing else makes the host wait)
+        self._h2d_done = torch.cuda.Event()
+        self._h2d_pending = False
         self._host_names = [n for n in ("obs", "node_obs", "adj", "reward", "done", "indiv_reward", "info")
                             if n in self.engine.out_slabs and not (self._lazy_info and n in ("indiv_reward", "info"))]
         self._host_t = [self._host_tensors(a) for a in self._arena]
@@ -249,6 +253,23 @@ class _BatchedVecEnv(ShareVecEnv):
         self.engine.step_host(src, pinned_actions, dev_actions, self._host_struct[self._flip], self._chunks)
         self._pending = self._arena[self._flip]
         self._flip ^= 1
+
+    def _pinned_reusable(self):
+        """Block until the last upload from the pinned action blocks has executed."""
+        if self._h2d_pending:
+            self._h2d_done.synchronize()
+            self._h2d_pending = False
+
+    def _uploaded(self):
+        self._h2d_done.record(torch.cuda.current_stream(self.engine.device))
+        self._h2d_pending = True
+
+    def _drain(self):
+        """Finish a pipelined host step whose results nobody collected (reset() after step_async)."""
+        if self._pending is not None:
+            self.engine.host_wait()
+            self._pending = None
+        self.waiting = False
 
     def _fetch(self):
         if self.output == "torch":
@@ -293,6 +314,8 @@ class _BatchedVecEnv(ShareVecEnv):
 
     # -- reference interface ------------------------------------------------------------
     def reset(self, num_current_episode: int = 0):
+        self._drain()   # a step still in flight must not have its arena handed out as the reset's
+        self._gen += 1  # infos of earlier steps can no longer be fetched
         self.engine.reset()
         return self._pack_obs(self._fetch())
 
@@ -311,9 +334,11 @@ class _BatchedVecEnv(ShareVecEnv):
         else:
             a = np.asarray(actions)
             if a.shape == (B, N) and np.issubdtype(a.dtype, np.integer):  # index fast path
+                self._pinned_reusable()
                 self._idx_pin.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)))
                 self.h2d_bytes_last = self._idx_pin.numel() * 4
                 eng.action_idx.copy_(self._idx_pin, non_blocking=True)
+                self._uploaded()
                 idx = eng.action_idx
             else:
                 if a.shape != (B, N, A):
@@ -328,8 +353,10 @@ class _BatchedVecEnv(ShareVecEnv):
                     self.waiting = True
                     return
                 # torch's threaded copy fills the pinned block ~15x faster than a numpy assignment
+                self._pinned_reusable()
                 self._act_pin[w].copy_(src)
                 self._act_dev[w].copy_(self._act_pin[w], non_blocking=True)
+                self._uploaded()
                 idx = eng.decode_onehot(self._act_dev[w])
         eng.step(idx)
         self.waiting = True
@@ -370,12 +397,18 @@ class _BatchedVecEnv(ShareVecEnv):
     # -- device-side statistics for the once-per-rollout reduction (dist.py) ---------------
     def episode_stats(self) -> torch.Tensor:
         """[sum reward, #agent collisions, #obstacle collisions, #agents done, #agents] of the
-        current step as a float64 device vector (reduced across GPUs by dist.reduce_stats)."""
-        o, st = self.engine.out, self.engine.state
-        cnt = st["agent_cnt"].to(torch.float64)
+        current step as a float64 device vector (reduced across GPUs by dist.reduce_stats).
+        The collision counts are the episode totals so far as this step's info rows report them
+        (july:806-829 Num_agent_collisions / Num_obst_collisions): a world that auto-reset this
+        step still shows the totals of the episode it just finished, whereas the state counters
+        have already been cleared for the new one.  Needs info=True."""
+        o = self.engine.out
+        if "info" not in o:
+            raise RuntimeError("episode_stats needs the info rows: construct the vec env with info=True")
+        info = o["info"].to(torch.float64)
         key = "indiv_reward" if "indiv_reward" in o else "reward"
-        return torch.stack([o[key].to(torch.float64).sum(), cnt[..., abi.AC_AGENT_COLL].sum(),
-                            cnt[..., abi.AC_OBST_COLL].sum(), o["done"].to(torch.float64).sum(),
+        return torch.stack([o[key].to(torch.float64).sum(), info[..., abi.INFO_KEYS.index("Num_agent_collisions")].sum(),
+                            info[..., abi.INFO_KEYS.index("Num_obst_collisions")].sum(), o["done"].to(torch.float64).sum(),
                             torch.tensor(float(self.num_envs * self.num_agents), dtype=torch.float64,
                                          device=self.engine.device)])
 

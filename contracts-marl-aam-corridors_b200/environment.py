@@ -112,9 +112,11 @@ class MultiAgentGraphEnv:
     def step(self, action_n: List):  # environment.py:1021-1063
         self.current_step += 1
         idx = actions_to_index(action_n, self.num_discrete_action, self.discrete_action_input)
-        self.world.step_actions(idx)  # _set_action + World.step + all scenario callbacks, fused
+        # environment.py:1022-1023: update_graph runs BEFORE _set_action / World.step, on the masked
+        # distances of the previous step -- world.edge_list after step() describes the pre-step graph
         if self.update_graph is not None:
             self.update_graph(self.world)
+        self.world.step_actions(idx)  # _set_action + World.step + all scenario callbacks, fused
         obs_n, reward_n, done_n, info_n = [], [], [], []
         node_obs_n, adj_n, agent_id_n = [], [], []
         for agent in self.agents:

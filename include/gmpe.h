@@ -10,11 +10,12 @@
  * Conventions
  *   - every buffer is CALLER-OWNED device memory (the Python host passes
  *     torch.Tensor.data_ptr()); the library never allocates outputs (its only own device
- *     memory is a 256/512-byte action table per handle).  Arrays of Real must be aligned to
+ *     memory is a 256/512-byte action table and one counter per handle).  Arrays of Real must be aligned to
  *     16 bytes, out.node_obs and out.info to 32 bytes (256-bit row stores);
  *   - 0 = ok, negative = error (GMPE_E_*), text via gmpe_last_error();
  *   - asynchronous on the caller's stream, no host synchronisation inside
- *     reset/step; one handle per device, not re-entrant, no internal threads;
+ *     reset/step; one handle per device, not re-entrant; the only internal threads are the
+ *     up-to-three helpers gmpe_step_host uses to stage a pageable action block;
  *   - `Real` below means float when GmpeConfig.precision == GMPE_F32 and double
  *     when GMPE_F64 (strict-parity instantiation);
  *   - all arrays are world-major, C-contiguous: [B][N][...] .
@@ -28,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GMPE_ABI_VERSION 10
+#define GMPE_ABI_VERSION 11
 
 /* error codes */
 #define GMPE_OK 0
@@ -69,6 +70,14 @@ extern "C" {
 #define GMPE_FLAG_INFO (1u << 5)            /* maintain + emit info_callback stats (july:741) */
 #define GMPE_FLAG_WALL_POINT_QUIRK (1u << 6)/* walls also act as point colliders (core.py:580) */
 #define GMPE_FLAG_CLASSIC_CONTACT (1u << 7) /* d_min = size_a+size_b (onpolicy/envs/mpe/core.py:282) */
+#define GMPE_FLAG_FORCE_TILE (1u << 8)      /* testing / A-B timing: run the generic tile kernel even where a
+                                               specialised lane-per-agent instantiation exists (ignored by the
+                                               rot-inv scenarios, which only that kernel serves) */
+
+/* GmpeConfig.formation -- args.formation_type (july:192, 492-497; multiagent/custom_scenarios/utils.py) */
+#define GMPE_FORMATION_POINT 0  /* set_landmarks_in_point  utils.py:165-193 */
+#define GMPE_FORMATION_LINE 1   /* set_landmarks_in_line   utils.py:77-131  */
+#define GMPE_FORMATION_CIRCLE 2 /* set_landmarks_in_circle utils.py:231-262 */
 
 #define GMPE_MAX_AGENTS 64
 #define GMPE_MAX_ENTITIES 160
@@ -148,6 +157,8 @@ typedef struct GmpeConfig {
   int32_t episode_length; /* world.world_length                       */
   int32_t total_actions;  /* A: 25 (unicycle/air_taxi), 5 or 9 (DI)   */
   uint32_t flags;
+  int32_t formation;      /* GMPE_FORMATION_* (tube scenarios; navigation_graph places goals at random) */
+  int32_t reserved0;      /* must be 0 */
   uint64_t seed;          /* Philox key                               */
   int64_t world_offset;   /* global index of local world 0 (multi-GPU sharding: RNG is invariant to G) */
   double world_size;
@@ -233,6 +244,15 @@ typedef struct GmpeStepInject {
   const GmpeState* reset_state; /* state to adopt instead of a Philox reset when a world auto-resets
                                (agent_state, agent_aux, world_f, landmarks, obstacles, walls are read;
                                flags/counters follow reset_world semantics)                            */
+  const double* reset_draws;    /* double [B][reset_draws_per_world] (device): uniform [0,1) numbers a
+                               world's reset consumes INSTEAD of its Philox stream, in the order
+                               reset_world draws from np.random (july:368 wall_length, :530 tube angle,
+                               then per spawn attempt jitter x, y (:467) and, when accepted, the heading
+                               of reset_velocity (core.py:328)); NaN / past the end = Philox.  Lets a
+                               reset be replayed on the reference's own random stream (reset parity);
+                               ignored when reset_state is given                                        */
+  int32_t reset_draws_per_world;
+  int32_t reserved0;
 } GmpeStepInject;
 
 typedef struct gmpe_ctx* gmpe_handle;
@@ -308,11 +328,18 @@ int gmpe_host_wait(gmpe_handle h);
  * train_mpe.py:31 with seed + rank*1000); world_offset as in GmpeConfig. */
 int gmpe_set_seed(gmpe_handle h, uint64_t seed, int64_t world_offset);
 
+/* Spawn placement is rejection sampling (july:452-486).  The reference loops until a draw fits;
+ * the kernels give up after 1024 rejected draws per entity, keep the last one and count the
+ * world here.  Reads (and optionally clears) the handle's device counter: synchronises the
+ * device, so not for the hot loop.  gmpe_create already refuses configurations whose agents
+ * cannot be packed (N * pi * (separation / 2)^2 > half of the spawn area). */
+int gmpe_placement_overflows(gmpe_handle h, int64_t* count, int clear);
+
 /* Number of kernel launches issued through this handle so far (bench gpu_launches). */
 int64_t gmpe_launch_count(gmpe_handle h);
 
 /* Name of the step kernel this handle launches (which mapping gmpe_create picked for the
- * configuration: "gmpe_step_coop_kernel", "gmpe_step_small_kernel" or "gmpe_step_kernel");
+ * configuration: "gmpe_step_coop_kernel" or "gmpe_step_kernel");
  * bench / profile bookkeeping only. */
 const char* gmpe_kernel_name(gmpe_handle h);
 

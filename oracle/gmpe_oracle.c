@@ -63,6 +63,8 @@ double gmpe_oracle_uniform01(uint64_t seed, int64_t world, uint32_t episode, uin
 static double uni(uint64_t seed, int64_t world, uint32_t ep, uint32_t idx, double lo, double hi) {
   return lo + (hi - lo) * gmpe_oracle_uniform01(seed, world, ep, idx); /* np.random.uniform */
 }
+/* bounded rejection sampling, as the kernels (gmpe_device.cuh): keep the last draw after this many */
+#define PLACE_MAX_ATTEMPTS 1024
 
 /* ------------------------------------------------------------------ small helpers */
 static double norm2(double x, double y) { return sqrt(x * x + y * y); } /* np.linalg.norm */
@@ -207,11 +209,39 @@ typedef struct {
   double* ob;    /* [O][2] */
   double* wl;    /* [W][4] */
   int32_t* ext;  /* [N][2] (three_phase: entry_reward_cooldown, spare) or NULL */
+  const double* draws; /* injected uniform [0,1) stream of this world's reset (GmpeStepInject.reset_draws) or NULL */
+  int ndraws;
+  int overflow;  /* a spawn rejection loop hit PLACE_MAX_ATTEMPTS */
   /* scratch for the current step */
   double pos[MAXE][2];
   double dist[MAXE][MAXE];
   double u[MAXN][2];
 } World;
+
+/* a uniform draw of world w's reset: the injected stream (the reference's own np.random draws,
+ * reset-parity tests) where it has an entry, Philox otherwise */
+static double wuni(const World* w, uint32_t idx, double lo, double hi) {
+  if (w->draws && (int)idx < w->ndraws && w->draws[idx] == w->draws[idx]) return lo + (hi - lo) * w->draws[idx];
+  return uni(w->c->seed, w->c->world_offset + w->b, (uint32_t)w->wi[GMPE_WI_EPISODE], idx, lo, hi);
+}
+
+/* GmpeConfig.formation: landmark l of L (july:492-497; utils.py:165-193 point, :77-131 line with
+ * np.linspace's arithmetic for a vector with a zero step component, :231-262 circle) */
+static void formation_landmark(const GmpeConfig* c, int l, int L, const double ext[2], double sa, double ca, double out[2]) {
+  double ws = c->world_size;
+  if (c->formation == GMPE_FORMATION_LINE) {
+    double start = -ws / 2, stop = ws / 2;
+    out[0] = (L > 1 && l == L - 1) ? stop : (L > 1 ? ((double)l / (double)(L - 1)) * (stop - start) + start : start);
+    out[1] = -ws / 2;
+  } else if (c->formation == GMPE_FORMATION_CIRCLE) {
+    double ang = (double)l * (2 * PI_D / (double)L);
+    out[0] = 0.0 + (ws / 3) * cos(ang);
+    out[1] = (ext[1] + ws / 5) + (ws / 3) * sin(ang);
+  } else {
+    out[0] = ext[0] + sa * (-ws / 3);
+    out[1] = ext[1] + ca * (-ws / 3);
+  }
+}
 
 static void bind_world(World* w, const GmpeConfig* c, const GmpeState* st, int64_t b) {
   w->c = c; w->b = b;
@@ -227,6 +257,7 @@ static void bind_world(World* w, const GmpeConfig* c, const GmpeState* st, int64
   w->ob = st->obstacles ? (double*)st->obstacles + b * w->O * 2 : NULL;
   w->wl = st->walls ? (double*)st->walls + b * w->W * GMPE_WALL_F : NULL;
   w->ext = st->agent_ext ? st->agent_ext + b * w->N * 2 : NULL;
+  w->draws = NULL; w->ndraws = 0; w->overflow = 0;
 }
 
 static int is_kin_heading(const GmpeConfig* c) { return c->dynamics != GMPE_DYN_DOUBLE_INTEGRATOR; }
@@ -936,15 +967,13 @@ static void tp_mask_adj(World* w) {
 /* random_scenario + setup_tube_params tp:416-587 */
 static void tp_random_scenario(World* w) {
   const GmpeConfig* c = w->c;
-  uint64_t seed = c->seed;
-  int64_t gw = c->world_offset + w->b;
-  uint32_t ep = (uint32_t)w->wi[GMPE_WI_EPISODE], idx = 0;
+  uint32_t idx = 0;
   double ws = c->world_size;
-  (void)uni(seed, gw, ep, idx++, 0.2, 0.8); /* wall_length draw, tp:343 (value unused) */
+  (void)wuni(w, idx++, 0.2, 0.8); /* wall_length draw, tp:343 (value unused) */
   double width = fmax(3 * c->entity_size * 2.5, ws * 0.15);
-  double angle = uni(seed, gw, ep, idx++, -PI_D / 2, PI_D / 2);
+  double angle = wuni(w, idx++, -PI_D / 2, PI_D / 2);
   double tl = ws * 0.8;
-  if (!is_corridor(w)) tl += uni(seed, gw, ep, idx++, -ws * 0.3, ws * 0.1); /* tp:503; fixed length in sc:537 */
+  if (!is_corridor(w)) tl += wuni(w, idx++, -ws * 0.3, ws * 0.1); /* tp:503; fixed length in sc:537 */
   double ca = cos(angle), sa = sin(angle);
   double ent[2] = {sa * (tl / 4), ca * (tl / 4)};
   double ext[2] = {sa * (-tl / 4), ca * (-tl / 4)};
@@ -956,26 +985,25 @@ static void tp_random_scenario(World* w) {
   w->wf[GMPE_WF_N_X] = (double)(float)(-e[1]); w->wf[GMPE_WF_N_Y] = (double)(float)e[0];
   w->wf[GMPE_WF_L] = L; w->wf[GMPE_WF_HALF_W] = width * 0.5;
   w->wf[GMPE_WF_WIDTH] = width; w->wf[GMPE_WF_ANGLE] = angle;
-  int k = 0;
+  int k = 0, tries = 0;
   while (k < w->N) { /* tp:424-443 */
-    double jx = 0.3 * uni(seed, gw, ep, idx, -ws, ws), jy = 0.3 * uni(seed, gw, ep, idx + 1, -ws, ws);
+    double jx = 0.3 * wuni(w, idx, -ws, ws), jy = 0.3 * wuni(w, idx + 1, -ws, ws);
     idx += 2;
     double d = (ws + k) / 3;
     double p[2] = {ent[0] + d * sa + jx, ent[1] + d * ca + jy};
     int bad = 0;
     for (int a = 0; a < k && !bad; ++a)
       if (norm2(w->as[a * 4] - p[0], w->as[a * 4 + 1] - p[1]) < c->separation_dist) bad = 1;
-    if (bad) continue;
+    if (bad && ++tries < PLACE_MAX_ATTEMPTS) continue;
+    if (bad) w->overflow = 1;
+    tries = 0;
     double* s = w->as + k * 4;
     s[0] = p[0]; s[1] = p[1];
-    if (is_kin_heading(c)) { s[2] = uni(seed, gw, ep, idx++, 0, TWO_PI); s[3] = c->v_min; }
+    if (is_kin_heading(c)) { s[2] = wuni(w, idx++, 0, TWO_PI); s[3] = c->v_min; }
     else { s[2] = 0; s[3] = 0; }
     ++k;
   }
-  for (int l = 0; l < w->L; ++l) { /* set_landmarks_in_point, utils.py:177-187 */
-    w->lm[l * 2] = ext[0] + sa * (-ws / 3);
-    w->lm[l * 2 + 1] = ext[1] + ca * (-ws / 3);
-  }
+  for (int l = 0; l < w->L; ++l) formation_landmark(c, l, w->L, ext, sa, ca, w->lm + l * 2); /* tp:459-464 */
 }
 
 /* ------------------------------------------------------------------ nav scenario (D1) */
@@ -1051,13 +1079,11 @@ static void reset_counters(World* w) { /* reset_world july:339-374 */
 /* random_scenario + setup_tube_params july:440-613, set_landmarks_in_point utils.py:165-193 */
 static void july_random_scenario(World* w) {
   const GmpeConfig* c = w->c;
-  uint64_t seed = c->seed;
-  int64_t gw = c->world_offset + w->b;
-  uint32_t ep = (uint32_t)w->wi[GMPE_WI_EPISODE], idx = 0;
+  uint32_t idx = 0;
   double ws = c->world_size;
-  (void)uni(seed, gw, ep, idx++, 0.2, 0.8); /* wall_length draw, july:368 (value unused) */
+  (void)wuni(w, idx++, 0.2, 0.8); /* wall_length draw, july:368 (value unused) */
   double width = fmax(3 * c->entity_size * 2.5, ws * 0.15);
-  double angle = uni(seed, gw, ep, idx++, -PI_D / 2, PI_D / 2);
+  double angle = wuni(w, idx++, -PI_D / 2, PI_D / 2);
   double tl = ws * 0.8, ca = cos(angle), sa = sin(angle);
   double ent[2] = {sa * (tl / 4), ca * (tl / 4)};
   double ext[2] = {sa * (-tl / 4), ca * (-tl / 4)};
@@ -1069,67 +1095,68 @@ static void july_random_scenario(World* w) {
   w->wf[GMPE_WF_N_X] = (double)(float)(-e[1]); w->wf[GMPE_WF_N_Y] = (double)(float)e[0];
   w->wf[GMPE_WF_L] = L; w->wf[GMPE_WF_HALF_W] = width * 0.5;
   w->wf[GMPE_WF_WIDTH] = width; w->wf[GMPE_WF_ANGLE] = angle;
-  int k = 0;
+  int k = 0, tries = 0;
   while (k < w->N) { /* july:452-486 */
-    double jx = 0.2 * uni(seed, gw, ep, idx, -ws, ws), jy = 0.2 * uni(seed, gw, ep, idx + 1, -ws, ws);
+    double jx = 0.2 * wuni(w, idx, -ws, ws), jy = 0.2 * wuni(w, idx + 1, -ws, ws);
     idx += 2;
     double d = (ws + k) / 5;
     double p[2] = {ent[0] + d * sa + jx, ent[1] + d * ca + jy};
     int bad = is_obstacle_collision(w, p, c->entity_size);
     for (int a = 0; a < k && !bad; ++a)
       if (norm2(w->as[a * 4] - p[0], w->as[a * 4 + 1] - p[1]) < c->separation_dist) bad = 1;
-    if (bad) continue;
+    if (bad && ++tries < PLACE_MAX_ATTEMPTS) continue;
+    if (bad) w->overflow = 1;
+    tries = 0;
     double* s = w->as + k * 4;
     s[0] = p[0]; s[1] = p[1];
-    if (is_kin_heading(c)) { s[2] = uni(seed, gw, ep, idx++, 0, TWO_PI); s[3] = c->v_min; }
+    if (is_kin_heading(c)) { s[2] = wuni(w, idx++, 0, TWO_PI); s[3] = c->v_min; }
     else { s[2] = 0; s[3] = 0; }
     ++k;
   }
-  for (int l = 0; l < w->L; ++l) { /* utils.py:177-187 */
-    w->lm[l * 2] = ext[0] + sa * (-ws / 3);
-    w->lm[l * 2 + 1] = ext[1] + ca * (-ws / 3);
-  }
+  for (int l = 0; l < w->L; ++l) formation_landmark(c, l, w->L, ext, sa, ca, w->lm + l * 2); /* july:492-497 */
 }
 
 /* nav reset (defined-by-build): obstacles, agents, goals at
  * 0.9*U(-ws/2, ws/2)^2 with the reference's rejection tests; 4 boundary walls. */
 static void nav_random_scenario(World* w) {
   const GmpeConfig* c = w->c;
-  uint64_t seed = c->seed;
-  int64_t gw = c->world_offset + w->b;
-  uint32_t ep = (uint32_t)w->wi[GMPE_WI_EPISODE], idx = 0;
+  uint32_t idx = 0;
   double ws = c->world_size, h = ws / 2;
   for (int q = 0; q < w->W; ++q) { /* q: 0 H top, 1 H bottom, 2 V right, 3 V left, then repeats */
     double* wl = w->wl + q * GMPE_WALL_F;
     wl[0] = (q & 2) ? 1.0 : 0.0; wl[1] = (q & 1) ? -h : h; wl[2] = -h; wl[3] = h;
   }
   for (int o = 0; o < w->O; ++o) {
-    w->ob[o * 2] = 0.9 * uni(seed, gw, ep, idx, -h, h); w->ob[o * 2 + 1] = 0.9 * uni(seed, gw, ep, idx + 1, -h, h);
+    w->ob[o * 2] = 0.9 * wuni(w, idx, -h, h); w->ob[o * 2 + 1] = 0.9 * wuni(w, idx + 1, -h, h);
     idx += 2;
   }
   int saveW = w->W; /* spawn rejection ignores the boundary walls' 1.5*size band except via the 0.9 factor */
-  int k = 0;
+  int k = 0, tries = 0;
   while (k < w->N) {
-    double p[2] = {0.9 * uni(seed, gw, ep, idx, -h, h), 0.9 * uni(seed, gw, ep, idx + 1, -h, h)};
+    double p[2] = {0.9 * wuni(w, idx, -h, h), 0.9 * wuni(w, idx + 1, -h, h)};
     idx += 2;
     int bad = is_obstacle_collision(w, p, c->entity_size);
     for (int a = 0; a < k && !bad; ++a)
       if (norm2(w->as[a * 4] - p[0], w->as[a * 4 + 1] - p[1]) < c->separation_dist) bad = 1;
-    if (bad) continue;
+    if (bad && ++tries < PLACE_MAX_ATTEMPTS) continue;
+    if (bad) w->overflow = 1;
+    tries = 0;
     double* s = w->as + k * 4;
     s[0] = p[0]; s[1] = p[1];
-    if (is_kin_heading(c)) { s[2] = uni(seed, gw, ep, idx++, 0, TWO_PI); s[3] = c->v_min; }
+    if (is_kin_heading(c)) { s[2] = wuni(w, idx++, 0, TWO_PI); s[3] = c->v_min; }
     else { s[2] = 0; s[3] = 0; }
     ++k;
   }
-  k = 0;
+  k = 0; tries = 0;
   while (k < w->L) {
-    double p[2] = {0.9 * uni(seed, gw, ep, idx, -h, h), 0.9 * uni(seed, gw, ep, idx + 1, -h, h)};
+    double p[2] = {0.9 * wuni(w, idx, -h, h), 0.9 * wuni(w, idx + 1, -h, h)};
     idx += 2;
     int bad = is_obstacle_collision(w, p, c->entity_size);
     for (int a = 0; a < k && !bad; ++a) /* is_landmark_collision july:916-925 */
       if (norm2(w->lm[a * 2] - p[0], w->lm[a * 2 + 1] - p[1]) < 1.2 * (2 * c->entity_size)) bad = 1;
-    if (bad) continue;
+    if (bad && ++tries < PLACE_MAX_ATTEMPTS) continue;
+    if (bad) w->overflow = 1;
+    tries = 0;
     w->lm[k * 2] = p[0]; w->lm[k * 2 + 1] = p[1];
     ++k;
   }
@@ -1188,6 +1215,11 @@ static void reset_world(World* w, const GmpeStepInject* inj, const GmpeStepOut* 
   const GmpeConfig* c = w->c;
   int odim = obs_dim_of(c), ndim = node_dim_of(c);
   reset_counters(w);
+  w->draws = NULL; w->ndraws = 0;
+  if (inj && inj->reset_draws && inj->reset_draws_per_world > 0) {
+    w->draws = inj->reset_draws + w->b * inj->reset_draws_per_world;
+    w->ndraws = inj->reset_draws_per_world;
+  }
   if (inj && inj->reset_state) adopt_injected(w, inj->reset_state);
   else {
     if (c->scenario == GMPE_SCEN_JULY_TUBE) july_random_scenario(w);
@@ -1269,6 +1301,13 @@ typedef struct {
   int64_t b0, b1;
 } Job;
 
+static long long g_overflows = 0; /* worlds whose placement gave up a rejection loop (gmpe_placement_overflows) */
+long long gmpe_oracle_overflows(int clear) {
+  long long v = __atomic_load_n(&g_overflows, __ATOMIC_RELAXED);
+  if (clear) __atomic_store_n(&g_overflows, 0, __ATOMIC_RELAXED);
+  return v;
+}
+
 static void* run_job(void* arg) {
   Job* j = (Job*)arg;
   World* w = (World*)malloc(sizeof(World));
@@ -1277,6 +1316,7 @@ static void* run_job(void* arg) {
     bind_world(w, j->cfg, j->st, b);
     if (j->is_reset) reset_world(w, j->inj, j->out);
     else step_world(w, j->act, j->inj, j->out, j->use_rk45);
+    if (w->overflow) __atomic_fetch_add(&g_overflows, 1, __ATOMIC_RELAXED);
   }
   free(w);
   return NULL;

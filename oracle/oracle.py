@@ -45,6 +45,8 @@ def lib():
         L.gmpe_oracle_integrate.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double]
         L.gmpe_oracle_uniform01.argtypes = [C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32]
         L.gmpe_oracle_uniform01.restype = C.c_double
+        L.gmpe_oracle_overflows.argtypes = [C.c_int]
+        L.gmpe_oracle_overflows.restype = C.c_longlong
         _lib = L
     return _lib
 
@@ -63,8 +65,11 @@ class OracleEnv:
         self._st = buffers.make_struct(abi.GmpeState, self.state)
         self._out = buffers.make_struct(abi.GmpeStepOut, self.out)
 
-    def reset(self, env_mask=None, reset_state: dict | None = None):
-        inj, keep = buffers.make_inject(None, reset_state)
+    def reset(self, env_mask=None, reset_state: dict | None = None, reset_draws=None):
+        if reset_draws is not None:
+            reset_draws = np.ascontiguousarray(reset_draws, dtype=np.float64)
+            assert reset_draws.ndim == 2 and reset_draws.shape[0] == self.cfg.num_worlds
+        inj, keep = buffers.make_inject(None, reset_state, reset_draws)
         m = None
         if env_mask is not None:
             m = np.ascontiguousarray(env_mask, dtype=np.uint8)
@@ -89,6 +94,11 @@ def integrate(dyn: int, use_rk45: bool, y, u, dt: float):
     u = np.array(u, dtype=np.float64)
     lib().gmpe_oracle_integrate(dyn, int(use_rk45), y.ctypes.data, u.ctypes.data, dt)
     return y
+
+
+def overflows(clear: bool = False) -> int:
+    """Worlds whose placement gave up a rejection loop since the last clear (process-wide)."""
+    return int(lib().gmpe_oracle_overflows(int(clear)))
 
 
 def uniform01(seed, world, episode, idx) -> float:

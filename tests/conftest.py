@@ -25,19 +25,17 @@ def pytest_collection_modifyitems(config, items):
 
 def pytest_generate_tests(metafunc):
     """Every GPU test runs once per kernel mapping: the one gmpe_create picks for the
-    configuration ("auto": lane-per-agent gmpe_coop.cuh for N = L = 3 worlds, the tile kernel
-    gmpe_step.cuh otherwise), the thread-per-world kernel (gmpe_small.cuh) and the tile kernel
-    forced, so every mapping stays pinned to the oracle."""
+    configuration ("auto": lane-per-agent gmpe_coop.cuh for worlds with 2 <= N = L <= 10 and no
+    obstacles / walls, the tile kernel gmpe_step.cuh otherwise) and the tile kernel forced
+    (GMPE_FLAG_FORCE_TILE), so both mappings stay pinned to the oracle."""
     if metafunc.definition.get_closest_marker("gpu") is not None:
         metafunc.fixturenames.append("kernel_variant")
-        metafunc.parametrize("kernel_variant", ["auto", "world", "tile"], indirect=True)
+        metafunc.parametrize("kernel_variant", ["auto", "tile"], indirect=True)
 
 
 @pytest.fixture
 def kernel_variant(request, monkeypatch):
-    monkeypatch.delenv("GMPE_FORCE_TILE", raising=False)
-    if request.param == "auto":
-        monkeypatch.delenv("GMPE_KERNEL", raising=False)
-    else:
-        monkeypatch.setenv("GMPE_KERNEL", request.param)
+    from gmpe_b200 import config
+
+    monkeypatch.setattr(config, "FORCE_TILE_DEFAULT", request.param == "tile")
     return request.param

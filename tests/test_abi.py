@@ -57,7 +57,7 @@ def test_header_constants_match_python_mirror():
 
 @pytest.mark.parametrize("kw", [
     dict(scenario_name="nav_metered_one_goal_graph_rotate_tube_july", dynamics_type="air_taxi", world_size=3),
-    dict(scenario_name="navigation_graph", num_agents=16, num_landmarks=16, num_obstacles=8, num_walls=4),
+    dict(scenario_name="navigation_graph", num_agents=16, num_landmarks=16, num_obstacles=8, num_walls=4, world_size=4),
 ])
 def test_gmpe_layout_matches_python_arithmetic(kw):
     lib = abi.load_library()

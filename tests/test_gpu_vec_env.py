@@ -142,7 +142,10 @@ def test_multi_agent_graph_env_replays_a_golden_episode_through_the_scenario_api
         np.testing.assert_allclose(np.array(rew_n), z["reward"][t], atol=tol)
         assert done_n == list(z["done"][t])
         assert info_n[1]["individual_reward"] == rew_n[1] and "Num_agent_collisions" in info_n[0]
-        assert (world.edge_list == z["edge_index"][t][:, :z["num_edges"][t]]).all()
+        # update_graph runs at the top of step() on the previous step's masked distances
+        # (environment.py:1022-1023); the trace stores the list of step t under index t
+        if t > 0:
+            assert (world.edge_list == z["edge_index"][t - 1][:, :z["num_edges"][t - 1]]).all()
         assert [int(i[0]) for i in id_n] == [0, 1, 2]
     assert t > 10
     with pytest.raises(AssertionError):
