@@ -38,7 +38,7 @@ class StagePool {
   // dst[0, n) = src[0, n), split over the helpers and the calling thread
   void copy(char* dst, const char* src, size_t n) {
     const size_t parts = th_.size() + 1;
-    if (n < (size_t)256 * 1024 || parts == 1) { memcpy(dst, src, n); return; }
+    if (n < (size_t)1024 * 1024 || parts == 1) { memcpy(dst, src, n); return; }  // waking the helpers costs more than a small copy
     const size_t chunk = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
     {
       std::lock_guard<std::mutex> g(m_);
@@ -108,7 +108,21 @@ struct gmpe_ctx {
   cudaEvent_t ev_tail = nullptr;
   bool tail_pending = false;
   StagePool* pool = nullptr;
+#ifdef GMPE_EXPERIMENTS
+  // GMPE_TRACE=1 (tools/e2e_sweep.py --trace): timeline of one host step, printed by gmpe_host_wait
+  std::vector<cudaEvent_t> tr_ev;   // [0] call start, then per slice: H2D done, kernels done, D2H done
+  std::vector<double> tr_host;      // per slice: staged, enqueued (us since the call); last: returned
+  std::vector<std::pair<int64_t, int64_t>> tr_sl;
+  bool tr_on = false;
+#endif
 };
+
+#ifdef GMPE_EXPERIMENTS
+#include <chrono>
+static double now_us() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#endif
 
 static thread_local std::string g_create_err;
 
@@ -608,20 +622,14 @@ int gmpe_decode_onehot_range(gmpe_handle h, const void* onehot, int elem_bytes, 
   return GMPE_OK;
 }
 
-// Slices of the batch for gmpe_step_host: multiples of 64 worlds (every slab of a slice stays
-// 16-byte aligned); the first slice is a quarter of the others -- nothing flows back over PCIe
-// until it has been staged, sent up and stepped.
+// Upload blocks of the batch for gmpe_step_host: `k` near-equal blocks of multiples of 64 worlds
+// (every slab of a block stays 16-byte aligned).
 static std::vector<std::pair<int64_t, int64_t>> host_slices(int64_t B, int k) {
   std::vector<std::pair<int64_t, int64_t>> out;
   const int64_t al = 64;
   if (k < 1 || B < 64 * al) k = 1;
-  if (k == 1) { out.push_back({0, B}); return out; }
-  int64_t first = (B / (4 * k - 3)) / al * al;
-  if (first < al) first = al;
-  int64_t step = (B - first + (k - 2)) / (k - 1);
-  step = (step + al - 1) / al * al;
-  out.push_back({0, first});
-  for (int64_t b0 = first; b0 < B; b0 += step) out.push_back({b0, std::min(B, b0 + step) - b0});
+  int64_t step = ((B + k - 1) / k + al - 1) / al * al;
+  for (int64_t b0 = 0; b0 < B; b0 += step) out.push_back({b0, std::min(B, b0 + step) - b0});
   return out;
 }
 
@@ -662,6 +670,17 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
     h->pool = new (std::nothrow) StagePool(hw >= 8 ? 3 : (hw >= 4 ? 1 : 0));
   }
   int rc = GMPE_OK;
+#ifdef GMPE_EXPERIMENTS
+  double tr_t0 = 0;
+  h->tr_on = getenv("GMPE_TRACE") && atoi(getenv("GMPE_TRACE"));
+  if (h->tr_on) {
+    while (h->tr_ev.size() < 3 * sl.size() + 1) { cudaEvent_t v; cudaEventCreate(&v); h->tr_ev.push_back(v); }
+    h->tr_host.assign(2 * sl.size() + 1, 0.0);
+    h->tr_sl = sl;
+    tr_t0 = now_us();
+    cudaEventRecord(h->tr_ev[0], main_s);
+  }
+#endif
   // a previous host step whose results were never collected: its copies read the device outputs
   if (e == cudaSuccess && h->tail_pending) e = cudaStreamWaitEvent(main_s, h->ev_tail, 0);
   if (e == cudaSuccess) {  // the copy-in stream starts behind whatever the caller has queued on its stream
@@ -675,8 +694,14 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
       if (h->pool) h->pool->copy((char*)actions_pinned + off, (const char*)actions_host + off, (size_t)nb);
       else memcpy((char*)actions_pinned + off, (const char*)actions_host + off, (size_t)nb);
     }
+#ifdef GMPE_EXPERIMENTS
+    if (h->tr_on) h->tr_host[2 * k] = now_us() - tr_t0;
+#endif
     e = cudaMemcpyAsync((char*)actions_dev + off, (const char*)actions_pinned + off, (size_t)nb, cudaMemcpyHostToDevice, h->s_in);
     if (e == cudaSuccess) e = cudaEventRecord(h->ev[2 * k], h->s_in);
+#ifdef GMPE_EXPERIMENTS
+    if (h->tr_on) cudaEventRecord(h->tr_ev[1 + 3 * k], h->s_in);
+#endif
     if (e == cudaSuccess) e = cudaStreamWaitEvent(main_s, h->ev[2 * k], 0);
     if (e != cudaSuccess) break;
     const int32_t* idx = action_kind == 0 ? (const int32_t*)actions_dev : idx_dev;
@@ -684,13 +709,27 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
     if (rc == GMPE_OK) rc = launch(h, MODE_STEP, st, idx, nullptr, nullptr, dev_out, cuda_stream, b0, cnt, true);
     if (rc != GMPE_OK) break;
     cudaSetDevice(h->device);  // (the calls above restore the caller's device)
-    e = cudaEventRecord(h->ev[2 * k + 1], main_s);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_out, h->ev[2 * k + 1], 0);
+#ifdef GMPE_EXPERIMENTS
+    if (h->tr_on) { cudaEventRecord(h->tr_ev[2 + 3 * k], main_s); h->tr_host[2 * k + 1] = now_us() - tr_t0; }
+#endif
+  }
+  // Results go back once every block has been uploaded and stepped, one copy per field over the
+  // whole batch: on the B200 boxes measured (profiles/r2_e2e_timeline.txt) a device->host copy that
+  // overlaps a host->device copy drops from ~50 GB/s to ~19 GB/s while the upload itself crawls at
+  // ~8 GB/s, and short per-slice copies reach 33-40 GB/s -- serial directions and long copies win.
+  if (e == cudaSuccess && rc == GMPE_OK) {
+    e = cudaEventRecord(h->ev[1], main_s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_out, h->ev[1], 0);
     for (int f = 0; f < 15 && e == cudaSuccess; ++f)
       if (dptr[f] && hptr[f])
-        e = cudaMemcpyAsync((char*)hptr[f] + b0 * bpw[f], (const char*)dptr[f] + b0 * bpw[f], (size_t)(cnt * bpw[f]),
-                            cudaMemcpyDeviceToHost, h->s_out);
+        e = cudaMemcpyAsync(hptr[f], dptr[f], (size_t)(B * bpw[f]), cudaMemcpyDeviceToHost, h->s_out);
+#ifdef GMPE_EXPERIMENTS
+    if (h->tr_on) for (size_t k = 0; k < sl.size(); ++k) cudaEventRecord(h->tr_ev[3 + 3 * k], h->s_out);
+#endif
   }
+#ifdef GMPE_EXPERIMENTS
+  if (h->tr_on) h->tr_host[2 * sl.size()] = now_us() - tr_t0;
+#endif
   if (e == cudaSuccess && rc == GMPE_OK) {
     e = cudaEventRecord(h->ev_tail, h->s_out);
     h->tail_pending = e == cudaSuccess;
@@ -707,6 +746,21 @@ int gmpe_host_wait(gmpe_handle h) {
   cudaError_t e = cudaStreamSynchronize(h->s_out);
   if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("gmpe_host_wait: ") + cudaGetErrorString(e));
   h->tail_pending = false;
+#ifdef GMPE_EXPERIMENTS
+  if (h->tr_on && !h->tr_sl.empty()) {
+    fprintf(stderr, "[trace] host step, %zu slices; device times in us since the call reached the stream\n", h->tr_sl.size());
+    for (size_t k = 0; k < h->tr_sl.size(); ++k) {
+      float a = 0, b = 0, c = 0;
+      cudaEventElapsedTime(&a, h->tr_ev[0], h->tr_ev[1 + 3 * k]);
+      cudaEventElapsedTime(&b, h->tr_ev[0], h->tr_ev[2 + 3 * k]);
+      cudaEventElapsedTime(&c, h->tr_ev[0], h->tr_ev[3 + 3 * k]);
+      fprintf(stderr, "[trace]  slice %zu worlds %6lld: host staged %7.1f enqueued %7.1f | dev H2D done %7.1f kernels done %7.1f D2H done %7.1f\n",
+              k, (long long)h->tr_sl[k].second, h->tr_host[2 * k], h->tr_host[2 * k + 1], a * 1e3, b * 1e3, c * 1e3);
+    }
+    fprintf(stderr, "[trace]  call returned at %7.1f us\n", h->tr_host[2 * h->tr_sl.size()]);
+    h->tr_sl.clear();
+  }
+#endif
   return GMPE_OK;
 }
 

@@ -232,7 +232,9 @@ class BatchedGraphMPE:
         b += 2 * (4 * N)               # agent_flags r+w
         b += 4 * N                     # action index in
         b += R * N + N                 # reward + done out
-        b += R * abi.WORLD_F + 2 * 4   # world frame in, step counter r+w
+        b += 2 * 4                     # step counter r+w
+        if c.scenario != abi.SCEN_NAV_GRAPH:
+            b += R * abi.WORLD_F       # tube frame in (navigation_graph has none: world_f is not read there)
         b += 2 * R * (L + O) + abi.WALL_F * R * W
         b += R * F * N + R * self.layout.node_dim * N * E + R * E * E
         if c.flags & abi.FLAG_INFO:

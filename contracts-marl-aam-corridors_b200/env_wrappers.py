@@ -204,11 +204,17 @@ class _BatchedVecEnv(ShareVecEnv):
         self._flip = 0
         self.h2d_bytes_last = 0
         self.d2h_bytes_last = nbytes
-        # Host-facing steps are PCIe-bound (one-hot block in, every tensor out).  Worlds are
-        # independent, so the batch is stepped in slices (gmpe_step_range): slice k's device->host
-        # copies run on their own stream while slice k+1's host->device copy and kernel proceed.
+        # Host-facing steps are PCIe-bound (one-hot block in, every tensor out): 7.9 MB up and 52.9 MB
+        # down per step at 65,536 navigation worlds.  Measured on the B200 boxes
+        # (profiles/r2_e2e_timeline.txt, profiles/r2_e2e_sweep.txt): copies in opposite directions that
+        # overlap slow each other down badly (device->host 50 -> 19 GB/s, host->device 8 GB/s), and
+        # short per-slice copies reach 33-40 GB/s -- so the default is the plain sequence: one
+        # threaded staging copy into pinned memory, one upload, decode + step, ONE download of the
+        # arena prefix (1.32 ms against a 1.02 ms copy-only ceiling).  pipeline_chunks > 1 routes the
+        # step through gmpe_step_host instead (staging / upload / kernels pipelined in that many blocks
+        # by the library's own helper threads; what a non-Python host would call).
         if pipeline_chunks is None:
-            pipeline_chunks = 4 if (output == "numpy" and B >= 8192) else 1
+            pipeline_chunks = 1
         # device-resident outputs have nothing to copy back: one launch, and no host copies in
         # flight that a later launch could overwrite
         self._chunks = max(1, int(pipeline_chunks)) if output == "numpy" else 1
@@ -219,6 +225,8 @@ class _BatchedVecEnv(ShareVecEnv):
         self._host_names = [n for n in ("obs", "node_obs", "adj", "reward", "done", "indiv_reward", "info")
                             if n in self.engine.out_slabs and not (self._lazy_info and n in ("indiv_reward", "info"))]
         self._host_t = [self._host_tensors(a) for a in self._arena]
+        #: numpy views of the two pinned arenas, built once (a step hands one of them out)
+        self._views = {a.data_ptr(): self._host_views(a) for a in self._arena}
         # the same pinned views as a GmpeStepOut of host pointers, for gmpe_step_host
         self._host_struct = [buffers.make_struct(abi.GmpeStepOut, t) for t in self._host_t]
         self._pending = None
@@ -247,9 +255,9 @@ class _BatchedVecEnv(ShareVecEnv):
         return out
 
     def _step_pipelined(self, src: torch.Tensor, pinned_actions: torch.Tensor, dev_actions: torch.Tensor):
-        """The batch in slices through ONE library call (gmpe_step_host): while slice k is stepped and
-        its outputs go back over PCIe, slice k+1 of the caller's action block (``src``, pageable) is
-        staged into pinned memory and sent up.  The copies of the results are in flight on return."""
+        """The batch through ONE library call (gmpe_step_host): the caller's action block (``src``,
+        pageable) is staged into pinned memory, sent up and stepped block by block, then every
+        host-visible field is copied back.  The copies of the results are in flight on return."""
         self.engine.step_host(src, pinned_actions, dev_actions, self._host_struct[self._flip], self._chunks)
         self._pending = self._arena[self._flip]
         self._flip ^= 1
@@ -278,14 +286,14 @@ class _BatchedVecEnv(ShareVecEnv):
             arena, self._pending = self._pending, None
             self.engine.host_wait()
             self._last_arena = arena
-            return self._host_views(arena)
+            return self._views[arena.data_ptr()]
         arena = self._arena[self._flip]
         self._flip ^= 1
         n = self._core_bytes
         arena[:n].copy_(self.engine.out_arena[:n], non_blocking=True)
         torch.cuda.current_stream(self.engine.device).synchronize()
         self._last_arena = arena
-        return self._host_views(arena)
+        return self._views[arena.data_ptr()]
 
     def _info_fetcher(self, arena: torch.Tensor):
         """Deferred device->host copy of this step's info rows (LazyInfos)."""
@@ -299,7 +307,7 @@ class _BatchedVecEnv(ShareVecEnv):
             arena[lo:hi].copy_(eng.out_arena[lo:hi], non_blocking=True)
             torch.cuda.current_stream(eng.device).synchronize()
             self.d2h_bytes_last += hi - lo
-            v = self._host_views(arena)
+            v = self._views[arena.data_ptr()]
             return v["info"], v["indiv_reward"]
         return fetch
 

@@ -305,13 +305,16 @@ int gmpe_decode_onehot_range(gmpe_handle h, const void* onehot, int elem_bytes, 
                              int64_t world_begin, int64_t world_count, void* cuda_stream);
 
 /* GraphSubprocVecEnv.step (onpolicy/envs/env_wrappers.py:959-1004) for a caller whose actions
- * and results live in HOST memory: the batch is cut into `slices` (the first one shorter, so
- * that results start to flow early) and for every slice the library stages the caller's action
- * block into page-locked memory, sends it up, decodes + steps the slice (gmpe_decode_onehot_range
- * + gmpe_step_range) and copies the slice of every field that is non-NULL in BOTH dev_out and
- * host_out back -- host->device copy, kernels and device->host copy of neighbouring slices
- * overlap on streams the handle owns.  The call returns when everything is ENQUEUED;
- * gmpe_host_wait blocks until the results are in host_out.  One host step in flight per handle.
+ * and results live in HOST memory.  The way up is pipelined: the batch is cut into `slices`
+ * blocks and for every block the library stages the caller's action block into page-locked
+ * memory (helper threads), sends it up and decodes + steps the block (gmpe_decode_onehot_range +
+ * gmpe_step_range), so that staging block k+1 overlaps the upload and the kernels of block k.
+ * The way down starts when the last block has been stepped: one copy per field that is non-NULL
+ * in BOTH dev_out and host_out over the whole batch (measured: copies in opposite directions at
+ * the same time, and short per-slice copies, both cost PCIe throughput on the B200 boxes --
+ * profiles/r2_e2e_timeline.txt).  Streams are owned by the handle.  The call returns when
+ * everything is ENQUEUED; gmpe_host_wait blocks until the results are in host_out.  One host
+ * step in flight per handle.
  *   actions_host   [B][N] int32 indices (action_kind 0) or [B][N][A] one-hot float / double
  *                  (action_kind 4 / 8), pageable or page-locked;
  *   actions_pinned page-locked staging block of the same size (may equal actions_host when

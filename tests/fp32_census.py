@@ -1,0 +1,254 @@
+"""Teacher-forced comparison of the fp32 CUDA step with the fp64 oracle that COUNTS what it
+cannot compare, instead of dropping it (VERDICT r1 "what's weak" #1).
+
+Every step the engine is loaded with the fp32 cast of the oracle's state, both sides take the
+same actions, and every output is compared world by world:
+
+  * discrete outputs (done, edge_index, num_edges, gnn_*) must be IDENTICAL, except in worlds
+    where a quantity that decides them sits within ``MARGIN`` of its threshold -- there fp32
+    and fp64 may legitimately land on different sides.  Those world-steps are counted, every
+    one of them must show such a quantity (``threshold_margin``), and their rate is bounded
+    by the caller;
+  * real outputs must agree to ``tol`` relative (1e-5, BASELINE.json north_star) in every
+    other world; the only further excuses are stated and counted too: a "two nearest agents"
+    ranking (july:1399-1415) or an agent-agent separation test (july:907-914) that hangs on a
+    gap below ``MARGIN`` (obs / reward / info of that world only), or an integer truncation of the
+    info row (july:756-770) of a value within ``MARGIN`` of an integer (info only).
+
+Test infrastructure: imported by tests/test_gpu_batch_vs_oracle.py and tools/fp32_census.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from gmpe_b200 import abi
+
+REAL_OUT = ("obs", "node_obs", "adj", "reward", "info", "edge_attr", "gnn_edge_attr")
+INT_OUT = ("done", "edge_index", "num_edges", "gnn_edge_index", "gnn_num_edges")
+
+#: A comparison `q < thr` may come out differently in fp32 when |q - thr| <= MARGIN * max(1, largest
+#: |coordinate| of the world): eight float32 ulps of the operands -- the cast of the teacher-forced
+#: state (1/2 ulp), one integration step (<= 9.4e-7 abs at |x| ~ 3) and the 2-ulp SFU
+#: sqrt / divide of the fp32 instantiation.  SURVEY H3 planned "1e-6 * thr".
+MARGIN = 1e-6
+
+
+def _entities(cfg, st):
+    P = st["agent_state"][..., :2]
+    parts = [P, st["landmarks"]]
+    if cfg.num_obstacles:
+        parts.append(st["obstacles"])
+    if cfg.num_walls:  # a wall's node sits at the midpoint of its segment
+        w = st["walls"]
+        mid = 0.5 * (w[..., 2] + w[..., 3])
+        horiz = w[..., 0] == 0
+        parts.append(np.stack([np.where(horiz, mid, w[..., 1]), np.where(horiz, w[..., 1], mid)], axis=-1))
+    return np.concatenate(parts, axis=1)
+
+
+def _min_abs(q, thresholds):
+    """min over the trailing axes of |q - thr| for every thr; q: (B, ...), thr scalar or (B,)."""
+    B = q.shape[0]
+    out = np.full(B, np.inf)
+    flat = q.reshape(B, -1)
+    for thr in thresholds:
+        t = np.asarray(thr, dtype=np.float64)
+        t = t.reshape(-1, 1) if t.ndim else t
+        out = np.minimum(out, np.abs(flat - t).min(axis=1))
+    return out
+
+
+def coordinate_scale(cfg, st):
+    ents = _entities(cfg, st)
+    return np.maximum(1.0, np.abs(ents).reshape(ents.shape[0], -1).max(axis=1))
+
+
+def threshold_margin(cfg, st, gnn=True):
+    """Per world: the smallest |q - thr| over the comparisons that decide the DISCRETE outputs of a
+    step taken into state ``st`` (positions after the physics), in units of the world's coordinate
+    scale.  Pair distances against the env-side and consumer-side edge radii (july:1660,
+    gnn_new.py:339); the distance to the own goal against the reach threshold (july:1186,
+    environment.py:264); the tube coordinates against every band of get_agent_phase (july:683-733,
+    621-637; three_phase_graph.py:592-705) -- the phase gates `reach`, hence `done` and the masks."""
+    N = cfg.num_agents
+    ents = _entities(cfg, st)
+    B, E = ents.shape[0], ents.shape[1]
+    iu = np.triu_indices(E, 1)
+    D = np.linalg.norm(ents[:, iu[0]] - ents[:, iu[1]], axis=-1)
+    D = np.where(D == 0.0, np.inf, D)  # coincident entities (point formation) are 0 in any precision
+    m = _min_abs(D, [cfg.coordination_range])
+    if gnn:
+        m = np.minimum(m, _min_abs(D, [cfg.gnn_max_edge_dist]))
+    P = st["agent_state"][..., :2]
+    d_goal = np.linalg.norm(P - st["landmarks"][:, :N], axis=-1)
+    m = np.minimum(m, _min_abs(d_goal, [cfg.goal_dist_thresh]))
+    if cfg.scenario != abi.SCEN_NAV_GRAPH:
+        wf = st["world_f"]
+        ent, ext = wf[:, None, abi.WF_ENT_X:abi.WF_ENT_Y + 1], wf[:, None, abi.WF_EXIT_X:abi.WF_EXIT_Y + 1]
+        e, n = wf[:, None, abi.WF_E_X:abi.WF_E_Y + 1], wf[:, None, abi.WF_N_X:abi.WF_N_Y + 1]
+        L, hw = wf[:, abi.WF_L], wf[:, abi.WF_HALF_W]
+        r = P.astype(np.float32).astype(np.float64) - ent  # july:624
+        s, y = (r * e).sum(-1), np.abs((r * n).sum(-1))
+        if cfg.scenario == abi.SCEN_JULY_TUBE:
+            bands = [-0.05, L + 0.05, -0.02 * L - 0.05, 0.08 * L + 0.05]
+            td = ext - ent
+            td = td / np.linalg.norm(td, axis=-1, keepdims=True)
+            passed = ((P - ext) * td).sum(-1)
+            m = np.minimum(m, _min_abs(passed, [0.0]))
+        else:
+            back = 0.05 if cfg.scenario == abi.SCEN_CORRIDOR_ROT_INV else 0.02
+            bands = [-0.05, L + 0.05, L, -0.02 * L - 0.05, 0.08 * L + 0.05, L - back * L - 0.05, L + 0.08 * L + 0.05]
+        m = np.minimum(m, _min_abs(s, bands))
+        m = np.minimum(m, _min_abs(y, [hw + 0.05]))
+    return m / coordinate_scale(cfg, st)
+
+
+def neighbour_tie_margin(cfg, st):
+    """Per world: the smallest gap between two candidates of an agent's "two nearest agents"
+    ranking (july:1399-1415, tp:1182-1196), in units of the coordinate scale."""
+    P = st["agent_state"][..., :2]
+    B, n = P.shape[0], P.shape[1]
+    if n < 3:
+        return np.full(B, np.inf)
+    D = np.linalg.norm(P[:, :, None] - P[:, None, :], axis=-1)
+    D[:, np.arange(n), np.arange(n)] = np.inf
+    S = np.sort(D, axis=-1)
+    gaps = np.diff(S[..., :min(3, n - 1)], axis=-1)
+    return gaps.reshape(B, -1).min(axis=1) / coordinate_scale(cfg, st)
+
+
+def separation_margin(cfg, st):
+    """Per world: the smallest | ||p_i - p_j|| - separation_dist | (is_collision, july:907-914:
+    a flip moves a reward by collision_rew and a counter of the info row by one)."""
+    P = st["agent_state"][..., :2]
+    n = P.shape[1]
+    if n < 2:
+        return np.full(P.shape[0], np.inf)
+    iu = np.triu_indices(n, 1)
+    D = np.linalg.norm(P[:, iu[0]] - P[:, iu[1]], axis=-1)
+    return _min_abs(D, [cfg.separation_dist]) / coordinate_scale(cfg, st)
+
+
+def info_truncation_margin(cfg, st):
+    """Per world: how close the info row's truncated quantities are to flipping -- the reference
+    keeps travelled distance and distance-left in int64 numpy arrays (july:756-770, float
+    assignments truncate), picks the nearest landmark by an argmin and tests it against the reach
+    threshold (july:745-770)."""
+    N = cfg.num_agents
+    pd = st["agent_aux"][..., 0]
+    # non-negative quantities: truncation can only flip at an integer >= 1
+    m = np.abs(pd - np.maximum(1.0, np.round(pd))).min(axis=1)
+    P = st["agent_state"][..., :2]
+    dal = np.linalg.norm(P[:, :, None] - st["landmarks"][:, None, :], axis=-1)  # (B, N, L)
+    S = np.sort(dal, axis=-1)
+    dmin = S[..., 0]
+    m = np.minimum(m, np.abs(dmin - np.maximum(1.0, np.round(dmin))).min(axis=1))
+    m = np.minimum(m, np.abs(dmin - cfg.goal_dist_thresh).min(axis=1))
+    if S.shape[-1] > 1:
+        gap = S[..., 1] - S[..., 0]
+        gap = np.where(gap == 0.0, np.inf, gap)  # coincident landmarks (point formation): the first index wins in any precision
+        m = np.minimum(m, gap.min(axis=1))
+    return m / coordinate_scale(cfg, st)
+
+
+class Census:
+    def __init__(self):
+        self.world_steps = 0
+        self.int_mismatch = 0            # world-steps whose discrete outputs differ
+        self.int_mismatch_margin_max = 0.0
+        self.int_mismatch_by_key = {k: 0 for k in INT_OUT}
+        self.tie_excused = 0             # world-steps whose obs differ only through a nearest-neighbour tie
+        self.sep_excused = 0             # ... whose reward / info differ through a separation test at the margin
+        self.trunc_excused = 0           # ... whose info row differs through an int truncation / nearest-landmark pick at the margin
+        self.near_threshold = 0          # world-steps with a deciding quantity inside MARGIN (whether they flipped or not)
+        self.max_rel_err = {k: 0.0 for k in REAL_OUT}
+
+    def as_dict(self):
+        d = dict(self.__dict__)
+        d["int_mismatch_rate"] = self.int_mismatch / max(1, self.world_steps)
+        d["margin"] = MARGIN
+        return d
+
+
+def _per_world_fail(a, b, tol):
+    err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    err = np.where(np.isnan(a) & np.isnan(b), 0.0, err)
+    err = np.where(np.isnan(err), np.inf, err)
+    flat = err.reshape(err.shape[0], -1)
+    return flat.max(axis=1) if flat.shape[1] else np.zeros(err.shape[0])
+
+
+def run_teacher_forced(cfg64, cfg32, acts, device=0, tol=1e-5, nthreads=8, label=""):
+    """Runs the comparison for len(acts) steps and returns a Census; raises AssertionError on any
+    difference that no stated margin accounts for."""
+    import torch
+
+    from gmpe_b200.engine import BatchedGraphMPE
+    from oracle.oracle import OracleEnv
+
+    orc = OracleEnv(cfg64, use_rk45=False, nthreads=nthreads)
+    # a copy that never auto-resets: its post-step state holds the positions at which the
+    # terminal step's reward / done were decided (the auto-reset overwrites them)
+    cfg_nr = cfg64.copy()
+    cfg_nr.flags &= ~abi.FLAG_AUTO_RESET
+    orc_nr = OracleEnv(cfg_nr, use_rk45=False, nthreads=nthreads)
+    eng = BatchedGraphMPE(cfg32, device)
+    orc.reset()
+    cs = Census()
+    B = cfg64.num_worlds
+    gnn = bool(cfg64.flags & abi.FLAG_GNN_EDGES)
+    for t in range(len(acts)):
+        eng.load_state_dict(orc.state)  # teacher forcing: fp32 cast of the oracle state
+        for k, v in orc.state.items():
+            orc_nr.state[k][...] = v
+        orc_nr.step(acts[t])
+        # a world that auto-resets this step re-draws from Philox in its own precision: inject the oracle's reset
+        o = orc.step(acts[t])
+        g = eng.step(torch.as_tensor(acts[t], device=eng.device), reset_state=orc.state)
+        g = {k: g[k].cpu().numpy() for k in REAL_OUT + INT_OUT if k in g}
+        cs.world_steps += B
+        # margins: at the decision positions of the step, and at the fresh positions of worlds that reset
+        marg = np.minimum(threshold_margin(cfg64, orc_nr.state, gnn), threshold_margin(cfg64, orc.state, gnn))
+        cs.near_threshold += int((marg <= MARGIN).sum())
+        flipped = np.zeros(B, dtype=bool)
+        for k in INT_OUT:
+            if k not in g:
+                continue
+            ne = (g[k] != o[k]).reshape(B, -1).any(axis=1)
+            cs.int_mismatch_by_key[k] += int(ne.sum())
+            flipped |= ne
+        if flipped.any():
+            worst = float(marg[flipped].max())
+            cs.int_mismatch_margin_max = max(cs.int_mismatch_margin_max, worst)
+            bad = np.where(flipped & (marg > MARGIN))[0]
+            assert bad.size == 0, (f"{label} t={t}: discrete outputs of world {int(bad[0])} differ from the oracle although no "
+                                   f"deciding quantity is within {MARGIN:g} of its threshold (closest: {marg[bad[0]]:.3e})")
+        cs.int_mismatch += int(flipped.sum())
+        tie = np.minimum(neighbour_tie_margin(cfg64, orc_nr.state), neighbour_tie_margin(cfg64, orc.state)) <= MARGIN
+        sep = separation_margin(cfg64, orc_nr.state) <= MARGIN
+        trunc = info_truncation_margin(cfg64, orc_nr.state) <= MARGIN
+        for k in REAL_OUT:
+            if k not in g:
+                continue
+            err = _per_world_fail(g[k].astype(np.float64), o[k], tol)
+            fail = err > tol
+            excuse = flipped.copy()
+            if k == "obs":
+                excuse |= tie
+            if k in ("reward", "info"):
+                excuse |= sep
+            if k == "info":
+                excuse |= trunc
+            ok = ~excuse
+            if ok.any():
+                cs.max_rel_err[k] = max(cs.max_rel_err[k], float(err[ok].max()))
+            bad = np.where(fail & ok)[0]
+            assert bad.size == 0, f"{label} t={t} {k}: world {int(bad[0])} off by {err[bad[0]]:.3e} relative (tol {tol:g})"
+            if k == "obs":
+                cs.tie_excused += int((fail & tie & ~flipped).sum())
+            if k == "reward":
+                cs.sep_excused += int((fail & sep & ~flipped).sum())
+            if k == "info":
+                cs.trunc_excused += int((fail & trunc & ~sep & ~flipped).sum())
+    eng.close()
+    return cs

@@ -293,9 +293,148 @@ def run_classic_trace(path, seed, T, num_agents=3, num_landmarks=3, pull=0.8):
           f"size={os.path.getsize(path)//1024}KB")
 
 
+def run_multiagent_force_trace(path, seed, T, num_agents=4, num_obstacles=3, wall_points=True, done_at=None):
+    """Stage-1 FORCE physics with the `multiagent` parameterisation: the reference's OWN
+    `World.apply_action_force / apply_environment_force / get_entity_collision_force /
+    get_wall_collision_force / integrate_state` (multiagent/core.py:766-964) -- dead code on the
+    live kinematic step, but callable -- driven unmodified in the classic step order
+    (onpolicy/envs/mpe/core.py:183-202) on a double-integrator world the harness assembles from the
+    reference's entity classes: agents, non-colliding landmarks, immovable obstacles, four wall
+    segments shorter than the box they frame (agents reach the end caps and walk around them).
+    `wall_points`: walls are members of world.entities (core.py:580) and therefore ALSO act as point
+    colliders at Wall.state.p_pos; the harness puts that point at the segment midpoint (the build's
+    GMPE_FLAG_WALL_POINT_QUIRK convention).  With wall_points=False the walls get collide=False --
+    only the segment force remains (the build's default).
+    `done_at`: from that step on agent 0 has status=True, zero velocity and the no-op action: the
+    reference suppresses the agent-agent force ON it (core.py:899-900) while the others still feel it."""
+    cwd = os.getcwd()
+    os.chdir(REFERENCE_ROOT)
+    try:
+        from multiagent.config import DoubleIntegratorConfig
+        from multiagent.core import Agent, Entity, EntityDynamicsType, Landmark, Wall, World
+    finally:
+        os.chdir(cwd)
+    rs = np.random.RandomState(seed)
+    N, O, h = num_agents, num_obstacles, 1.0
+    # P3 (SURVEY G5): World.__init__ reads config_class.COORDINATION_RANGE, which the DI config lacks
+    DoubleIntegratorConfig.COORDINATION_RANGE = DoubleIntegratorConfig.COMMUNICATION_RANGE
+    world = World(EntityDynamicsType.DoubleIntegratorXY)
+    world.agents = [Agent(EntityDynamicsType.DoubleIntegratorXY) for _ in range(N)]
+    for i, a in enumerate(world.agents):
+        a.id, a.name, a.collide, a.status, a.max_speed = i, f"agent {i}", True, False, 2  # july:283-291 (args.max_speed)
+        a.action.u = np.zeros(2)
+    world.landmarks = [Landmark() for _ in range(N)]
+    for i, l in enumerate(world.landmarks):
+        l.id, l.name, l.collide, l.movable = i, f"landmark {i}", False, False  # july:295-300
+    world.obstacles = [Entity() for _ in range(O)]
+    for i, o in enumerate(world.obstacles):
+        o.id, o.name, o.collide, o.movable = i, f"obstacle {i}", True, False   # july:302-309
+    segs = [("H", h, (-0.6 * h, 0.6 * h)), ("H", -h, (-0.6 * h, 0.6 * h)), ("V", h, (-0.6 * h, 0.6 * h)), ("V", -h, (-0.6 * h, 0.6 * h))]
+    world.walls = [Wall(orient=o, axis_pos=a, endpoints=e) for o, a, e in segs]
+    for i, w in enumerate(world.walls):
+        w.id, w.name, w.collide, w.movable = i, f"wall {i}", bool(wall_points), False  # july:317-321
+        mid = 0.5 * (w.endpoints[0] + w.endpoints[1])
+        w.state.p_pos = np.array([mid, w.axis_pos]) if w.orient == "H" else np.array([w.axis_pos, mid])
+    for o in world.obstacles:
+        o.state.p_pos = rs.uniform(-0.55 * h, 0.55 * h, 2)
+    for l in world.landmarks:
+        l.state.p_pos = rs.uniform(-0.8 * h, 0.8 * h, 2)
+    placed = []
+    for a in world.agents:  # spawn clear of the obstacles and of each other (bounded rejection)
+        for attempt in range(10000):
+            p = rs.uniform(-0.85 * h, 0.85 * h, 2)
+            if all(np.linalg.norm(p - q) > 0.52 for q in [o.state.p_pos for o in world.obstacles] + placed):
+                break
+        else:
+            raise RuntimeError("could not place the agents")
+        placed.append(p.copy())
+        a.state.p_pos = p
+        a.state.p_vel = np.zeros(2)
+    ag = world.agents
+    init_state = np.array([[*a.state.p_pos, *a.state.p_vel] for a in ag])
+    u_tab = np.array([[0, 0], [1, 0], [-1, 0], [0, 1], [0, -1]], dtype=np.float64) * 5.0  # environment.py:399-409, 460-463
+    dmin = DoubleIntegratorConfig.COLLISION_DISTANCE
+    acts, states, status = [], [], []
+    n_agent = n_done = n_obst = n_wall = n_cap = 0
+
+    def toward(d):
+        return (1 if d[0] > 0 else 2) if abs(d[0]) > abs(d[1]) else (3 if d[1] > 0 else 4)
+
+    for t in range(T):
+        if done_at is not None and t == done_at:
+            ag[0].status = True
+            ag[0].state.p_vel = np.zeros(2)  # DoubleIntegratorXYState.reset_velocity
+        a_idx = []
+        for a in ag:
+            if a.status:
+                k = 0
+            else:
+                r = rs.rand()
+                if r < 0.35:    # chase the nearest other agent
+                    tgt = min((o for o in ag if o is not a), key=lambda o: np.linalg.norm(o.state.p_pos - a.state.p_pos))
+                    k = toward(tgt.state.p_pos - a.state.p_pos)
+                elif r < 0.55:  # run into the nearest obstacle
+                    tgt = min(world.obstacles, key=lambda o: np.linalg.norm(o.state.p_pos - a.state.p_pos))
+                    k = toward(tgt.state.p_pos - a.state.p_pos)
+                elif r < 0.85:  # head for the end of the nearest wall segment
+                    p = a.state.p_pos
+                    k = toward(np.array([np.sign(p[0]) * (0.6 * h if abs(p[1]) > abs(p[0]) else h) - p[0],
+                                         np.sign(p[1]) * (h if abs(p[1]) > abs(p[0]) else 0.6 * h) - p[1]]))
+                else:
+                    k = int(rs.randint(5))
+            a_idx.append(k)
+            a.action.u = u_tab[k].copy()
+        # statistics of the configuration the forces are evaluated on
+        for i in range(N):
+            for j in range(i + 1, N):
+                if np.linalg.norm(ag[i].state.p_pos - ag[j].state.p_pos) < dmin:
+                    n_agent += 1
+                    n_done += int(bool(ag[i].status) or bool(ag[j].status))
+            n_obst += sum(np.linalg.norm(ag[i].state.p_pos - o.state.p_pos) < dmin for o in world.obstacles)
+            for w in world.walls:
+                prll, perp = (0, 1) if w.orient == "H" else (1, 0)
+                p = ag[i].state.p_pos
+                if w.endpoints[0] - ag[i].size <= p[prll] <= w.endpoints[1] + ag[i].size and abs(p[perp] - w.axis_pos) < ag[i].size + 0.5 * w.width:
+                    n_wall += 1
+                    n_cap += int(p[prll] < w.endpoints[0] or p[prll] > w.endpoints[1])
+        # classic World.step order (onpolicy/envs/mpe/core.py:183-202) on the multiagent force functions
+        p_force = [None] * len(world.entities)
+        p_force = world.apply_action_force(p_force)
+        p_force = world.apply_environment_force(p_force)
+        world.integrate_state(p_force)
+        acts.append(a_idx)
+        states.append([[*a.state.p_pos, *a.state.p_vel] for a in ag])
+        status.append([int(bool(a.status)) for a in ag])
+    out = dict(init_agent_state=init_state, init_landmarks=np.array([l.state.p_pos for l in world.landmarks]),
+               obstacles=np.array([o.state.p_pos for o in world.obstacles]),
+               walls=np.array([[0.0 if w.orient == "H" else 1.0, w.axis_pos, w.endpoints[0], w.endpoints[1]] for w in world.walls]),
+               actions=np.array(acts, dtype=np.int32), state=np.array(states), status=np.array(status, dtype=np.uint8),
+               T=T, size=float(ag[0].size), dt=float(world.dt), damping=float(world.damping),
+               contact_force=float(world.contact_force), contact_margin=float(world.contact_margin),
+               wall_contact_force=float(world.wall_contact_force), wall_contact_margin=float(world.wall_contact_margin),
+               wall_width=float(world.walls[0].width), collision_distance=float(dmin), max_speed=float(ag[0].max_speed),
+               wall_points=int(bool(wall_points)), done_at=-1 if done_at is None else int(done_at),
+               num_agents=N, num_landmarks=N, num_obstacles=O, num_walls=len(world.walls))
+    np.savez_compressed(path, **out)
+    print(f"{os.path.basename(path)}: multiagent force step N={N} O={O} W=4 T={T}: pair-steps inside COLLISION_DISTANCE {n_agent} "
+          f"(with the done agent {n_done}), obstacle {n_obst}, wall contacts {n_wall} (end caps {n_cap}) "
+          f"size={os.path.getsize(path)//1024}KB")
+
+
+MULTIAGENT_FORCE_TRACES = (
+    ("multiagent_force_n4_o3_w4_s51.npz", dict(seed=51, T=200, done_at=100)),
+    ("multiagent_force_n4_o3_w4_nopoint_s52.npz", dict(seed=52, T=200, wall_points=False, done_at=120)),
+    ("multiagent_force_n6_o4_w4_s53.npz", dict(seed=53, T=150, num_agents=6, num_obstacles=4)),
+)
+
+
 def main():
     install_shims()
     g = lambda name: os.path.join(HERE, name)
+    if "--multiagent-force" in sys.argv:  # only the traces added in round 2
+        for name, kw in MULTIAGENT_FORCE_TRACES:
+            run_multiagent_force_trace(g(name), **kw)
+        return
     # C3: july / air_taxi / N=3 -- README.md:84-105 flags
     run_july_trace(g("july_n3_pursuit_s1.npz"), seed=1, T=200, policy="pursuit")
     run_july_trace(g("july_n3_pursuit_s2.npz"), seed=2, T=200, policy="pursuit", eps=0.3)
@@ -343,6 +482,9 @@ def main():
     # stage-1 force physics: the live classic-MPE World.step
     run_classic_trace(g("classic_spread_n3_s11.npz"), seed=11, T=120)
     run_classic_trace(g("classic_spread_n6_s12.npz"), seed=12, T=80, num_agents=6, num_landmarks=6)
+    # ... and the multiagent/core.py force functions themselves: walls, obstacles, a done agent
+    for name, kw in MULTIAGENT_FORCE_TRACES:
+        run_multiagent_force_trace(g(name), **kw)
 
 
 if __name__ == "__main__":

@@ -11,6 +11,8 @@ import torch
 from gmpe_b200 import abi, default_args, make_config
 from oracle.oracle import OracleEnv
 
+import fp32_census
+
 pytestmark = pytest.mark.gpu
 
 CASES = {
@@ -66,30 +68,13 @@ CASES = {
                                         dynamics_type="double_integrator", world_size=3, episode_length=12,
                                         goal_rew=30, collaborative=False, total_actions=9), B=200, T=20),
 }
-REAL_OUT = ("obs", "node_obs", "adj", "reward", "info", "edge_attr", "gnn_edge_attr")
-INT_OUT = ("done", "edge_index", "num_edges", "gnn_edge_index", "gnn_num_edges")
+REAL_OUT, INT_OUT = fp32_census.REAL_OUT, fp32_census.INT_OUT
 
 
 def _cfg(case, precision):
     kw = dict(CASES[case].get("kw", {}))
     return make_config(default_args(**CASES[case]["args"]), CASES[case]["B"], precision=precision, seed=7,
                        world_offset=3, gnn_edges=True, **kw)
-
-
-def _neighbour_ties(state, eps=1e-5):
-    """Worlds where some agent's nearest-neighbour ranking (the "two nearest agents" of the
-    observation, july:1399-1415, tp:1182-1196) hangs on a distance gap below fp32 resolution:
-    either order is a correct fp32 answer, so those worlds are left out of the real-valued
-    comparison for that step."""
-    P = state["agent_state"][..., :2]
-    n = P.shape[1]
-    if n < 3:
-        return np.zeros(P.shape[0], dtype=bool)
-    D = np.linalg.norm(P[:, :, None] - P[:, None, :], axis=-1)
-    D[:, np.arange(n), np.arange(n)] = np.inf
-    S = np.sort(D, axis=-1)
-    gaps = np.diff(S[..., :min(3, n - 1)], axis=-1)
-    return (gaps < eps).any(axis=(1, 2))
 
 
 def _actions(cfg, T, seed):
@@ -150,34 +135,25 @@ def test_fp64_free_running_with_auto_reset(case):
     eng.close()
 
 
+#: fp32 and fp64 may decide a threshold comparison differently when the compared quantity is
+#: within fp32_census.MARGIN of the threshold.  Such world-steps are counted, each one is
+#: checked to have that quantity, and their number is bounded: a world-step holds O(E^2 / 2)
+#: pair distances spread over O(world_size), so about E^2 * MARGIN of them are expected to
+#: sit that close -- RATE_BOUND allows 4x that, plus one for the small-sample cases.
+def _int_mismatch_bound(cfg, world_steps):
+    E = cfg.num_agents + cfg.num_landmarks + cfg.num_obstacles + cfg.num_walls
+    return 1 + int(4 * E * E * fp32_census.MARGIN * world_steps)
+
+
 @pytest.mark.parametrize("case", list(CASES))
 def test_fp32_teacher_forced_per_step(case):
-    from gmpe_b200.engine import BatchedGraphMPE
-
+    """fp32 production kernels, teacher-forced from the oracle state every step: reals within
+    1e-5 relative (north_star), discrete outputs identical except where a deciding quantity is
+    within MARGIN of its threshold -- counted, verified and bounded (fp32_census.py)."""
     cfg64 = _cfg(case, "fp64")
     cfg32 = _cfg(case, "fp32")
-    T = CASES[case]["T"]
-    acts = _actions(cfg64, T, 13)
-    orc = OracleEnv(cfg64, use_rk45=False, nthreads=8)
-    eng = BatchedGraphMPE(cfg32, 0)
-    orc.reset()
-    bad_worlds = np.zeros(cfg64.num_worlds, dtype=bool)
-    for t in range(T):
-        eng.load_state_dict(orc.state)  # teacher forcing: fp32 cast of the oracle state
-        # a world that auto-resets this step re-draws from Philox in its own precision: inject the oracle's reset
-        pre = {k: v.copy() for k, v in orc.state.items()}
-        o = orc.step(acts[t])
-        g = eng.step(torch.as_tensor(acts[t], device="cuda"), reset_state=orc.state)
-        for k in INT_OUT:
-            ne = (g[k].cpu().numpy() != o[k]).reshape(cfg64.num_worlds, -1).any(axis=1)
-            bad_worlds |= ne
-        ok = ~bad_worlds & ~_neighbour_ties(orc.state)
-        for k in REAL_OUT:
-            a = g[k].cpu().numpy().astype(np.float64)[ok]
-            b = o[k][ok]
-            tol = 1e-5 if k != "reward" else 2e-5
-            m = (np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b))) | (np.isnan(a) & np.isnan(b))
-            assert m.all(), f"{case} t={t} {k}: max |diff| {np.nanmax(np.abs(a - b)):.3e}"
-        bad_worlds[:] = False  # teacher forcing re-synchronises every step
-        del pre
-    eng.close()
+    acts = _actions(cfg64, CASES[case]["T"], 13)
+    cs = fp32_census.run_teacher_forced(cfg64, cfg32, acts, tol=1e-5, label=case)
+    print("fp32 census", case, cs.as_dict())
+    assert cs.int_mismatch <= _int_mismatch_bound(cfg64, cs.world_steps), cs.as_dict()
+    assert cs.tie_excused + cs.sep_excused + cs.trunc_excused <= 1 + int(1e-4 * cs.world_steps), cs.as_dict()
