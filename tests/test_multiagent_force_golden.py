@@ -58,14 +58,23 @@ def test_traces_exist_and_exercise_every_contact():
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p))
-def test_oracle_force_step_matches_multiagent_core(path):
+@pytest.mark.parametrize("teacher", [True, False], ids=["teacher_forced", "free_running"])
+def test_oracle_force_step_matches_multiagent_core(path, teacher):
+    """Teacher-forced from the trace every step: 1e-13 over the whole episode (measured: <= 7e-16,
+    i.e. the restatement IS the reference's arithmetic).  Free-running: 1e-10 over the first 55
+    steps -- the contacts are stiff (3e2 / 2e-2) and amplify a last-ulp difference by ~1.2x per step
+    (1e-16 at step 50 -> 3e-6 at step 150 in trace s51), so a bound over the whole episode would
+    test chaos, not the restatement."""
     z = np.load(path)
     env = OracleEnv(_cfg(z, "fp64"))
     env.reset(reset_state=_reset_state(z, np.float64))
     done_at = int(z["done_at"])
     worst = 0.0
-    for t in range(int(z["T"])):
+    prev = z["init_agent_state"]
+    for t in range(int(z["T"]) if teacher else 55):
         live = slice(None)
+        if teacher:
+            env.state["agent_state"][0] = prev
         if 0 <= done_at <= t:  # agent.status = True (what reward() does on goal reach, july:1188-1190)
             env.state["agent_flags"][0, 0, abi.AF_STATUS] = 1
             env.state["agent_state"][0, 0] = (z["state"][t - 1][0] if t > done_at else
@@ -73,7 +82,8 @@ def test_oracle_force_step_matches_multiagent_core(path):
             live = slice(1, None)
         env.step(z["actions"][t][None])
         worst = max(worst, float(np.abs(env.state["agent_state"][0, live] - z["state"][t][live]).max()))
-    assert worst <= 1e-10, worst  # the live agents free-run over the whole episode, through every contact
+        prev = z["state"][t]
+    assert worst <= (1e-13 if teacher else 1e-10), worst
 
 
 @pytest.mark.gpu
