@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # error codes
 OK, E_INVALID, E_CUDA, E_NULL = 0, -1, -2, -3
@@ -118,7 +118,7 @@ EXPORTED_SYMBOLS = (
     "gmpe_abi_version", "gmpe_create", "gmpe_destroy", "gmpe_last_error", "gmpe_layout",
     "gmpe_reset", "gmpe_step", "gmpe_decode_onehot", "gmpe_launch_count", "gmpe_set_seed",
     "gmpe_kernel_name", "gmpe_step_range", "gmpe_decode_onehot_range", "gmpe_step_host", "gmpe_host_wait",
-    "gmpe_placement_overflows",
+    "gmpe_placement_overflows", "gmpe_gnn_flatten", "gmpe_gnn_flat_scratch_elems",
 )
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -175,6 +175,11 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.gmpe_kernel_name.restype = C.c_char_p
     lib.gmpe_placement_overflows.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
     lib.gmpe_placement_overflows.restype = C.c_int
+    lib.gmpe_gnn_flat_scratch_elems.argtypes = [C.c_void_p]
+    lib.gmpe_gnn_flat_scratch_elems.restype = C.c_int64
+    lib.gmpe_gnn_flatten.argtypes = [C.c_void_p, C.POINTER(GmpeStepOut), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+    lib.gmpe_gnn_flatten.restype = C.c_int
     lib.gmpe_set_seed.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
     lib.gmpe_set_seed.restype = C.c_int
     v = lib.gmpe_abi_version()

@@ -15,6 +15,7 @@
 #include "gmpe_coop.cuh"
 #include "gmpe_coop_table.h"
 #include "gmpe_step.cuh"
+#include "gmpe_flat.cuh"
 
 using namespace gmpe;
 
@@ -737,6 +738,45 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
   if (prev != h->device) cudaSetDevice(prev);
   if (rc != GMPE_OK) return rc;
   if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("gmpe_step_host: ") + cudaGetErrorString(e));
+  return GMPE_OK;
+}
+
+int64_t gmpe_gnn_flat_scratch_elems(gmpe_handle h) {
+  if (!h) return 0;
+  const int64_t B = h->cfg.num_worlds;
+  return B + (B + kFlatBlock - 1) / kFlatBlock + 1;
+}
+
+int gmpe_gnn_flatten(gmpe_handle h, const GmpeStepOut* out, int64_t* flat_edge_index, void* flat_edge_attr, int64_t capacity,
+                     int64_t* total, int64_t* scratch, void* cuda_stream) {
+  if (!h) return GMPE_E_NULL;
+  if (!out || !flat_edge_index || !flat_edge_attr || !total || !scratch) return fail(h, GMPE_E_NULL, "gmpe_gnn_flatten: NULL argument");
+  if (!out->gnn_edge_index || !out->gnn_edge_attr || !out->gnn_num_edges)
+    return fail(h, GMPE_E_NULL, "gmpe_gnn_flatten: out.gnn_edge_index / gnn_edge_attr / gnn_num_edges missing (GMPE_FLAG_GNN_EDGES)");
+  if (capacity < 1) return fail(h, GMPE_E_INVALID, "gmpe_gnn_flatten: capacity must be positive");
+  const GmpeConfig& c = h->cfg;
+  const int64_t B = c.num_worlds;
+  const int N = c.num_agents, E = N + c.num_landmarks + c.num_obstacles + c.num_walls, cap = E * (E - 1);
+  const int nblk = (int)((B + kFlatBlock - 1) / kFlatBlock);
+  int64_t* local = scratch;
+  int64_t* block_pre = scratch + B;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  flat_scan_blocks<<<nblk, kFlatBlock, 0, s>>>(out->gnn_num_edges, B, local, block_pre);
+  flat_scan_tops<<<1, kFlatBlock, 0, s>>>(block_pre, nblk, N, total);
+  const int grid = (int)std::min<int64_t>((B + 7) / 8, (int64_t)h->sm_count * 8);
+  if (c.precision == GMPE_F64)
+    flat_expand<double><<<grid, 256, 0, s>>>(out->gnn_edge_index, (const double*)out->gnn_edge_attr, out->gnn_num_edges, local, block_pre,
+                                            B, N, E, cap, flat_edge_index, flat_edge_index + capacity, (double*)flat_edge_attr, capacity);
+  else
+    flat_expand<float><<<grid, 256, 0, s>>>(out->gnn_edge_index, (const float*)out->gnn_edge_attr, out->gnn_num_edges, local, block_pre,
+                                           B, N, E, cap, flat_edge_index, flat_edge_index + capacity, (float*)flat_edge_attr, capacity);
+  cudaError_t e = cudaGetLastError();
+  if (prev != h->device) cudaSetDevice(prev);
+  if (e != cudaSuccess) return fail(h, GMPE_E_CUDA, std::string("gmpe_gnn_flatten: ") + cudaGetErrorString(e));
+  h->launches += 3;
   return GMPE_OK;
 }
 

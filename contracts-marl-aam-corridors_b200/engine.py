@@ -210,6 +210,35 @@ class BatchedGraphMPE:
         self._keep = (onehot,)
         return out
 
+    def gnn_flat_edges(self, capacity: int | None = None, out_struct=None):
+        """The consumer-side edge list of the last step in the layout ``GNNBase.forward`` consumes
+        (gnn_new.py:492-500 -> process_adj :328-358 on the (B*N, E, E) stack): ``edge_index`` int64
+        (2, nnz) with node ids ``(world * N + agent) * E + entity`` in (graph, row, col) order and
+        ``edge_attr`` (nnz, 1).  Built on the device from the step kernel's per-world list (scan +
+        gather); reading ``nnz`` is the one host synchronisation, as in ``Tensor.nonzero``.
+        Needs ``gnn_edges=True``.  The results are views of buffers the engine reuses."""
+        if "gnn_edge_index" not in self.out:
+            raise abi.GmpeError("gnn_flat_edges needs the consumer-side edge list: make_config(..., gnn_edges=True)")
+        cap_max = self.B * self.N * self.layout.edge_cap
+        capacity = cap_max if capacity is None else int(capacity)
+        buf = getattr(self, "_flat", None)
+        if buf is None or buf[0].shape[1] < capacity:
+            with torch.cuda.device(self.device):
+                n_scratch = int(self.lib.gmpe_gnn_flat_scratch_elems(self._h))
+                buf = (torch.empty((2, capacity), dtype=torch.int64, device=self.device),
+                       torch.empty((capacity,), dtype=self.real, device=self.device),
+                       torch.zeros((1,), dtype=torch.int64, device=self.device),
+                       torch.empty((n_scratch,), dtype=torch.int64, device=self.device))
+            self._flat = buf
+        ei, ea, total, scratch = buf
+        rc = self.lib.gmpe_gnn_flatten(self._h, C.byref(self._out if out_struct is None else out_struct), ei.data_ptr(),
+                                       ea.data_ptr(), ei.shape[1], total.data_ptr(), scratch.data_ptr(), self._stream())
+        self._check(rc, "gmpe_gnn_flatten")
+        nnz = int(total.item())
+        if nnz > ei.shape[1]:
+            raise abi.GmpeError(f"gnn_flat_edges: {nnz} edges do not fit the capacity of {ei.shape[1]}")
+        return ei[:, :nnz], ea[:nnz].unsqueeze(1)
+
     # -- checkpoint / teacher forcing (SURVEY section 5) ---------------------------------
     def state_dict(self) -> dict:
         return {k: v.clone() for k, v in self.state.items()}

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GMPE_ABI_VERSION 11
+#define GMPE_ABI_VERSION 12
 
 /* error codes */
 #define GMPE_OK 0
@@ -326,6 +326,22 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
                    void* actions_pinned, void* actions_dev, int32_t* idx_dev, const GmpeStepOut* dev_out,
                    const GmpeStepOut* host_out, int slices, void* cuda_stream);
 int gmpe_host_wait(gmpe_handle h);
+
+/* The consumer-side edge list in the layout the consumer takes: what GNNBase.forward
+ * (onpolicy/algorithms/utils/gnn_new.py:492-500) gets from process_adj (:328-358) on the
+ * (B*N, E, E) stack of adjacency matrices -- one graph per (world, agent), the N graphs of a world
+ * sharing one matrix.  From out->gnn_edge_index / gnn_edge_attr / gnn_num_edges of the last step:
+ *   flat_edge_index  int64 [2][capacity] (device): row 0 sources, row 1 targets, node id =
+ *                    (world * N + agent) * E + entity, edges in (graph, row, col) order;
+ *   flat_edge_attr   Real  [capacity]: the distance (edge_dim = 1, environment.py:997);
+ *   total            int64 [1] (device): nnz over all B*N graphs.  Entries [total, capacity) are not
+ *                    written; when total > capacity nothing may be read (raise capacity: at most
+ *                    B * N * E * (E - 1));
+ *   scratch          int64 [gmpe_gnn_flat_scratch_elems(h)] (device).
+ * Three launches (scan of the per-world counts, gather), asynchronous on the caller's stream. */
+int64_t gmpe_gnn_flat_scratch_elems(gmpe_handle h);
+int gmpe_gnn_flatten(gmpe_handle h, const GmpeStepOut* out, int64_t* flat_edge_index, void* flat_edge_attr,
+                     int64_t capacity, int64_t* total, int64_t* scratch, void* cuda_stream);
 
 /* Re-key the Philox streams: replaces env.seed(seed) (environment.py:219-223, called by
  * train_mpe.py:31 with seed + rank*1000); world_offset as in GmpeConfig. */
