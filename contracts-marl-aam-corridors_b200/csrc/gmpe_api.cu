@@ -97,6 +97,7 @@ struct gmpe_ctx {
   int small;  // KERNEL_TILE (gmpe_step.cuh) / KERNEL_COOP (gmpe_coop.cuh)
   const void* fn;
   int64_t resident;  // CTAs of the step kernel that fit on the device at once
+  unsigned char act_tab_host[512];  // the same table for the kernel parameter block (KParams::act_tab_c)
   void* act_tab;  // device copy of the _set_action table (Real [32][2]) followed by the placement-overflow counter
                   // (one 64-bit word at byte ACT_TAB_BYTES): the only device memory the library owns
   int64_t launches;
@@ -427,6 +428,8 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
       tf[2 * a] = f0; tf[2 * a + 1] = f1;
     }
     const size_t nbytes = f64 ? sizeof(td) : sizeof(tf);
+    memset(h->act_tab_host, 0, sizeof(h->act_tab_host));
+    memcpy(h->act_tab_host, f64 ? (const void*)td : (const void*)tf, nbytes);
     static_assert(sizeof(td) <= ACT_TAB_BYTES, "action table");
     e = cudaMalloc(&h->act_tab, ACT_TAB_BYTES + 8);
     if (e == cudaSuccess) e = cudaMemset(h->act_tab, 0, ACT_TAB_BYTES + 8);
@@ -550,6 +553,12 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
     grid = grid_for(h, p.num_tiles);
   }
   p.stage_graph = h->stage_graph;
+  memcpy(p.act_tab_c, h->act_tab_host, sizeof(p.act_tab_c));
+  if (h->small == KERNEL_COOP) {  // round structure of the persistent grid (num_tiles counts CTAs of GMPE_COOP_WARPS warps)
+    const int wpw = 32 / c.num_agents;
+    p.coop_groups = (int)((p.c.num_worlds + wpw - 1) / wpw);
+    p.coop_full_rounds = p.coop_groups / (grid * GMPE_COOP_WARPS);
+  }
   const int N = c.num_agents, L = c.num_landmarks, O = c.num_obstacles, W = c.num_walls;
   p.E = N + L + O + W;
   p.F = obs_dim_of(c);

@@ -48,6 +48,13 @@ struct KParams {
   const double* reset_draws;  // GmpeStepInject.reset_draws (already re-based on the launch's first world) or nullptr
   int reset_draws_n;          // ... doubles per world
   unsigned long long* overflow_cnt;  // worlds whose placement gave up a rejection loop (device counter owned by the handle)
+  // lane-per-agent kernel (gmpe_coop.cuh): the round structure of the persistent grid, worked out
+  // on the host (the 64-bit divisions cost ~150 instructions at the head of every warp), and the
+  // _set_action table itself (Real [32][2]) so that the lookup is a constant-bank load instead of
+  // a second dependent global load behind the action index
+  int coop_groups;       // ceil(worlds of the launch / worlds per warp)
+  int coop_full_rounds;  // coop_groups / (grid * warps per CTA)
+  alignas(16) unsigned char act_tab_c[512];
 };
 
 // ---- shared memory carve-up --------------------------------------------------------
