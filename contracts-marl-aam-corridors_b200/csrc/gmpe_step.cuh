@@ -547,9 +547,10 @@ __device__ __forceinline__ void pad_edges(int32_t* ei, Real* ea, int n, int cap,
 }
 
 // ---- the kernel ----------------------------------------------------------------------
-// Launch bounds picked by tools/sweep.py on a B200 (profiles/r1_sweep.txt): 128 threads with
-// >= 7 resident CTAs per SM (<= 72 registers) beat 256 x 1..4 and 128 x 3..6, 8 on the large-world
-// workloads (latency-bound: resident warps matter more than the extra spills).
+// Launch bounds picked on a B200: 128 threads with >= 5 resident CTAs per SM (<= 96 registers).
+// Round 1 (profiles/r1_sweep.txt) ran 7 CTAs at 72 registers; with the kernel as it is now the spills
+// at 72 cost more than the warps bring (profiles/r2_sweep.txt: N = 16: 247 -> 235 us, N = 64:
+// 437 -> 420 us with 5; 4 and 3 are slower again, 6 and 8 as slow as 7).
 #ifndef GMPE_TILE_NODE_ROWWISE_MIN_E  // node rows: warp per (world, ego) from this many entities on
 #define GMPE_TILE_NODE_ROWWISE_MIN_E 64
 #endif
@@ -564,7 +565,7 @@ constexpr int kEdgeUnroll = GMPE_EDGE_UNROLL;
 #define GMPE_LB_THREADS 128
 #endif
 #ifndef GMPE_LB_MINBLOCKS
-#define GMPE_LB_MINBLOCKS 7
+#define GMPE_LB_MINBLOCKS 5
 #endif
 // NC / LC / OC / WC > 0: entity counts known at compile time (instantiated for the BASELINE
 // shapes 16/16/8/4 and 64/64/0/0 in fp32); NC == 0: every count is a launch-time value.
