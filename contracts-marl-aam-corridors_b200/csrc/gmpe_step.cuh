@@ -561,6 +561,10 @@ __device__ __forceinline__ void pad_edges(int32_t* ei, Real* ea, int n, int cap,
 #define GMPE_EDGE_UNROLL 2
 #endif
 constexpr int kEdgeUnroll = GMPE_EDGE_UNROLL;
+#ifndef GMPE_NODE_UNROLL
+#define GMPE_NODE_UNROLL 1
+#endif
+constexpr int kNodeUnroll = GMPE_NODE_UNROLL;
 #ifndef GMPE_LB_THREADS
 #define GMPE_LB_THREADS 128
 #endif
@@ -1058,6 +1062,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
       // smaller worlds: element-parallel over (world, ego j, entity k), one 256-bit store each
       Real* g_node = (Real*)p.out.node_obs + (size_t)w0 * N * E * 8;
       const int total = nw * N * E;
+#pragma unroll kNodeUnroll
       for (int q = tid; q < total; q += nthr) {
         uint32_t k, t2, j, w;
         dE.divmod(q, t2, k);
