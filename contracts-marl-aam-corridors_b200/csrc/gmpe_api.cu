@@ -3,6 +3,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <sched.h>
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -19,14 +22,19 @@
 
 using namespace gmpe;
 
-// Staging of a pageable action block into page-locked memory (gmpe_step_host) on a few helper
-// threads: a single-threaded memcpy moves ~10 GB/s, which put 0.8 ms of copy in front of a
-// 1.3 ms step for the runner's 7.9 MB float64 one-hot block.  The helpers are created on the
-// first host step that needs staging and sleep on a condition variable in between.
+// Staging of a pageable action block into page-locked memory (gmpe_step_host) by a few helper
+// threads plus the caller: a single-threaded memcpy moves ~10 GB/s, which would put 0.8 ms of copy
+// in front of a 1.3 ms step for the runner's 7.9 MB float64 one-hot block.  The copy is cut into
+// 256 KB pieces handed out IN ORDER through an atomic counter, and every piece raises a flag when it
+// is done: the caller starts the job, then for each upload block of the step waits (copying pieces
+// itself meanwhile) only until the pieces of THAT block are in place -- the upload of block k and
+// its kernels run while the helpers are still staging block k+1.  The helpers are created on the
+// first host step that needs staging; between steps they poll for a few milliseconds, then sleep.
 class StagePool {
  public:
-  explicit StagePool(int helpers) {
-    for (int t = 0; t < helpers; ++t) th_.emplace_back([this, t] { run(t); });
+  enum { PIECE = 256 * 1024, MAX_PIECES = 4096 };
+  explicit StagePool(int helpers) : done_(new std::atomic<uint8_t>[MAX_PIECES]) {
+    for (int t = 0; t < helpers; ++t) th_.emplace_back([this] { run(); });
   }
   ~StagePool() {
     {
@@ -35,52 +43,98 @@ class StagePool {
     }
     cv_.notify_all();
     for (auto& t : th_) t.join();
+    delete[] done_;
   }
-  // dst[0, n) = src[0, n), split over the helpers and the calling thread
-  void copy(char* dst, const char* src, size_t n) {
-    const size_t parts = th_.size() + 1;
-    if (n < (size_t)1024 * 1024 || parts == 1) { memcpy(dst, src, n); return; }  // waking the helpers costs more than a small copy
-    const size_t chunk = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
-    {
-      std::lock_guard<std::mutex> g(m_);
-      dst_ = dst; src_ = src; n_ = n; chunk_ = chunk;
-      pending_ = (int)th_.size();
-      ++gen_;
+  // dst[0, n) = src[0, n), asynchronously; wait_until(bytes) / finish() below
+  void start(char* dst, const char* src, size_t n) {
+    {  // a helper that woke late for the previous job has left it before the job variables change
+      std::unique_lock<std::mutex> g(m_);
+      idle_.wait(g, [this] { return active_ == 0; });
     }
-    cv_.notify_all();
-    if (n > chunk * th_.size()) memcpy(dst + chunk * th_.size(), src + chunk * th_.size(), n - chunk * th_.size());
-    std::unique_lock<std::mutex> g(m_);
-    done_.wait(g, [this] { return pending_ == 0; });
+    npieces_ = (n + PIECE - 1) / PIECE;
+    if (npieces_ > MAX_PIECES) npieces_ = 0;  // (never at these sizes) -> the caller copies everything in wait_until
+    dst_ = dst; src_ = src; n_ = n;
+    for (size_t q = 0; q < npieces_; ++q) done_[q].store(0, std::memory_order_relaxed);
+    next_.store(0, std::memory_order_relaxed);
+    if (npieces_ > 1 && !th_.empty()) {
+      {
+        std::lock_guard<std::mutex> g(m_);
+        active_ = (int)th_.size();
+        ++gen_;
+        gen_atomic_.store(gen_, std::memory_order_release);
+      }
+      cv_.notify_all();
+    }
+    waited_ = 0;
   }
+  // returns once dst[0, upto) is complete
+  void wait_until(size_t upto) {
+    if (npieces_ == 0) {  // job too large for the flag table: plain copy of the missing part
+      if (upto > waited_) { memcpy(dst_ + waited_, src_ + waited_, upto - waited_); waited_ = upto; }
+      return;
+    }
+    const size_t last = (upto + PIECE - 1) / PIECE;  // pieces [0, last) are needed
+    for (size_t q = waited_; q < last; ++q) {
+      while (!done_[q].load(std::memory_order_acquire)) {
+        if (!copy_one()) std::this_thread::yield();
+      }
+    }
+    if (last > waited_) waited_ = last;
+  }
+  void finish() { wait_until(n_); }  // every piece is in place: no helper touches the buffers any more
 
  private:
-  void run(int t) {
+  bool copy_one() {
+    const size_t q = next_.fetch_add(1, std::memory_order_relaxed);
+    if (q >= npieces_) return false;
+    const size_t lo = q * (size_t)PIECE;
+    memcpy(dst_ + lo, src_ + lo, std::min((size_t)PIECE, n_ - lo));
+    done_[q].store(1, std::memory_order_release);
+    return true;
+  }
+  void run() {
     uint64_t seen = 0;
     for (;;) {
-      char* d; const char* s; size_t n, c;
-      {
+      // A rollout steps every ~1.3 ms: between steps a helper polls the generation counter for a few
+      // milliseconds before it goes to sleep -- waking a sleeping thread costs 0.1 - 1 ms on these boxes,
+      // more than the whole staging copy (OpenMP runtimes spin between parallel regions for the same reason).
+      bool got = false;
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int spin = 0;; ++spin) {
+        if (gen_atomic_.load(std::memory_order_acquire) != seen) { got = true; break; }
+        if ((spin & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(4)) break;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      if (!got) {
         std::unique_lock<std::mutex> g(m_);
         cv_.wait(g, [&] { return quit_ || gen_ != seen; });
         if (quit_) return;
-        seen = gen_;
-        d = dst_; s = src_; n = n_; c = chunk_;
       }
-      const size_t lo = c * (size_t)t;
-      if (lo < n) memcpy(d + lo, s + lo, std::min(c, n - lo));
       {
         std::lock_guard<std::mutex> g(m_);
-        if (--pending_ == 0) done_.notify_one();
+        if (quit_) return;
+        seen = gen_;
+      }
+      while (copy_one()) {}
+      {
+        std::lock_guard<std::mutex> g(m_);
+        if (--active_ == 0) idle_.notify_one();
       }
     }
   }
   std::vector<std::thread> th_;
   std::mutex m_;
-  std::condition_variable cv_, done_;
+  std::condition_variable cv_, idle_;
+  std::atomic<uint8_t>* done_;
+  std::atomic<size_t> next_{0};
   char* dst_ = nullptr;
   const char* src_ = nullptr;
-  size_t n_ = 0, chunk_ = 0;
+  size_t n_ = 0, npieces_ = 0, waited_ = 0;
   uint64_t gen_ = 0;
-  int pending_ = 0;
+  std::atomic<uint64_t> gen_atomic_{0};
+  int active_ = 0;
   bool quit_ = false;
 };
 
@@ -676,9 +730,13 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
   }
   if (e == cudaSuccess && !h->ev_tail) e = cudaEventCreateWithFlags(&h->ev_tail, cudaEventDisableTiming);
   if (actions_pinned != actions_host && !h->pool) {
-    const unsigned hw = std::thread::hardware_concurrency();
-    h->pool = new (std::nothrow) StagePool(hw >= 8 ? 3 : (hw >= 4 ? 1 : 0));
+    unsigned hw = std::thread::hardware_concurrency();
+    cpu_set_t cs;  // the cores this process may run on (a rank pinned to its share of the box), not the box
+    if (sched_getaffinity(0, sizeof(cs), &cs) == 0 && CPU_COUNT(&cs) > 0) hw = (unsigned)CPU_COUNT(&cs);
+    h->pool = new (std::nothrow) StagePool(hw >= 16 ? 7 : (hw >= 8 ? 3 : (hw >= 4 ? 2 : (hw >= 2 ? 1 : 0))));
   }
+  const bool staging = actions_pinned != actions_host;
+  if (staging && h->pool) h->pool->start((char*)actions_pinned, (const char*)actions_host, (size_t)(B * act_bpw));
   int rc = GMPE_OK;
 #ifdef GMPE_EXPERIMENTS
   double tr_t0 = 0;
@@ -700,8 +758,8 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
   for (size_t k = 0; k < sl.size() && e == cudaSuccess && rc == GMPE_OK; ++k) {
     const int64_t b0 = sl[k].first, cnt = sl[k].second;
     const int64_t off = b0 * act_bpw, nb = cnt * act_bpw;
-    if (actions_pinned != actions_host) {
-      if (h->pool) h->pool->copy((char*)actions_pinned + off, (const char*)actions_host + off, (size_t)nb);
+    if (staging) {
+      if (h->pool) h->pool->wait_until((size_t)(off + nb));
       else memcpy((char*)actions_pinned + off, (const char*)actions_host + off, (size_t)nb);
     }
 #ifdef GMPE_EXPERIMENTS
@@ -723,6 +781,7 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
     if (h->tr_on) { cudaEventRecord(h->tr_ev[2 + 3 * k], main_s); h->tr_host[2 * k + 1] = now_us() - tr_t0; }
 #endif
   }
+  if (staging && h->pool) h->pool->finish();  // also on the error paths: no helper may outlive the caller's buffers
   // Results go back once every block has been uploaded and stepped, one copy per field over the
   // whole batch: on the B200 boxes measured (profiles/r2_e2e_timeline.txt) a device->host copy that
   // overlaps a host->device copy drops from ~50 GB/s to ~19 GB/s while the upload itself crawls at

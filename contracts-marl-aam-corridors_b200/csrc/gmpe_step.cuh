@@ -561,6 +561,10 @@ __device__ __forceinline__ void pad_edges(int32_t* ei, Real* ea, int n, int cap,
 #define GMPE_EDGE_UNROLL 2
 #endif
 constexpr int kEdgeUnroll = GMPE_EDGE_UNROLL;
+#ifndef GMPE_EDGE_UNROLL_MID  // compile-time shapes of up to 64 entities (the 16/16/8/4 instance): 236 -> 226 us with 8, N = 64 is best with 2
+#define GMPE_EDGE_UNROLL_MID 8
+#endif
+constexpr int kEdgeUnrollMid = GMPE_EDGE_UNROLL_MID;
 #ifndef GMPE_NODE_UNROLL
 #define GMPE_NODE_UNROLL 1
 #endif
@@ -1194,7 +1198,7 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
             offm |= (uint32_t)(!h || mk[h ? cg : 0] != 0) << g;
           }
           int n_env = 0, n_gnn = 0;
-#pragma unroll kEdgeUnroll
+#pragma unroll (EC > 0 && EC <= 64 ? kEdgeUnrollMid : kEdgeUnroll)
           for (int r = 0; r < E; ++r) {
             const V2 a = pw[r];
             const bool mr = mk[r] != 0;

@@ -20,11 +20,12 @@ sys.path.insert(0, ROOT)
 spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "contracts-marl-aam-corridors_b200/csrc/build.py"))
 b = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(b)
-so = os.path.join(ROOT, "build", "variants", "lib_experiments.so")
-os.makedirs(os.path.dirname(so), exist_ok=True)
-if "--no-build" not in sys.argv:
-    b.build(force=True, out=so, defines=("GMPE_EXPERIMENTS",))
-os.environ["GMPE_LIB"] = so
+if "--trace" in sys.argv:  # the timeline print-out lives in GMPE_EXPERIMENTS builds only
+    so = os.path.join(ROOT, "build", "variants", "lib_experiments.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    if "--no-build" not in sys.argv:
+        b.build(force=True, out=so, defines=("GMPE_EXPERIMENTS",))
+    os.environ["GMPE_LIB"] = so
 
 import torch  # noqa: E402
 
