@@ -34,6 +34,12 @@ namespace gmpe {
 #ifndef GMPE_COOP_MINBLOCKS_NAV  // navigation_graph, fp32, N = 3: the lightest per-lane state -- 80 registers, 6 CTAs per SM
 #define GMPE_COOP_MINBLOCKS_NAV 6     // (28.6 us against 30.2 us with 5 at 65,536 worlds; july is slower with 6: profiles/r2_sweep.txt)
 #endif
+#ifndef GMPE_COOP_MINBLOCKS_N4  // fp32, N = 4, 5: two_phase N = 5 at 65,536 worlds 70.4 us with 3, 65.7 us with 4, 83.5 us with 2
+#define GMPE_COOP_MINBLOCKS_N4 4
+#endif
+#ifndef GMPE_COOP_MINBLOCKS_N6  // fp32, N = 6 .. 10: three_phase N = 10 at 32,768 worlds 130 us with 2, 139 us with 3
+#define GMPE_COOP_MINBLOCKS_N6 2
+#endif
 #ifndef GMPE_COOP_MINBLOCKS_TP  // rot-inv family, fp32, N = 3 (heavier per-lane state than july / navigation)
 #define GMPE_COOP_MINBLOCKS_TP 4
 #endif
@@ -91,7 +97,7 @@ struct CoopTraits {
   // resident CTAs still fit in shared memory, else they share one and B waits for A to drain.
   // resident CTAs asked of the compiler: the register budget has to grow with the per-lane
   // world image (positions, goals, velocities and two distance rows of 2N entries)
-  static constexpr int MINBLOCKS = N > 5 ? (R == 4 ? 2 : 1) : (N > 3 ? (R == 4 ? 3 : 2) : (R == 4 ? (ROT_INV ? GMPE_COOP_MINBLOCKS_TP : (SCEN == GMPE_SCEN_NAV_GRAPH ? GMPE_COOP_MINBLOCKS_NAV : GMPE_COOP_MINBLOCKS_F32)) : GMPE_COOP_MINBLOCKS_F64));
+  static constexpr int MINBLOCKS = N > 5 ? (R == 4 ? GMPE_COOP_MINBLOCKS_N6 : 1) : (N > 3 ? (R == 4 ? GMPE_COOP_MINBLOCKS_N4 : 2) : (R == 4 ? (ROT_INV ? GMPE_COOP_MINBLOCKS_TP : (SCEN == GMPE_SCEN_NAV_GRAPH ? GMPE_COOP_MINBLOCKS_NAV : GMPE_COOP_MINBLOCKS_F32)) : GMPE_COOP_MINBLOCKS_F64));
   static constexpr bool SPLIT = GMPE_COOP_BULK_STORE && (up16(ROUND_A + ROUND_B) + 0) * GMPE_COOP_WARPS * MINBLOCKS <= 220 * 1024;
   static constexpr int B_OFF = SPLIT ? ROUND_A : 0;
   static constexpr int SLAB_BYTES = SPLIT ? up16(ROUND_A + ROUND_B) : up16(ROUND_A > ROUND_B ? ROUND_A : ROUND_B);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Back-to-back step time of one configuration (no L2 flush), e.g. to compare kernel mappings:
-   GMPE_KERNEL=tile python tools/quick_step_time.py nav_metered_one_goal_graph_rotate_tube_july 8 32768"""
+   python tools/quick_step_time.py nav_metered_one_goal_graph_rotate_tube_july 8 32768 [tile]"""
 import os
 import sys
 
@@ -13,6 +13,9 @@ from gmpe_b200 import default_args, make_config  # noqa: E402
 from gmpe_b200.engine import BatchedGraphMPE  # noqa: E402
 
 scen, n, B = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+if len(sys.argv) > 4 and sys.argv[4] == "tile":
+    from gmpe_b200 import config as _config
+    _config.FORCE_TILE_DEFAULT = True
 dyn = "double_integrator" if scen == "navigation_graph" else "air_taxi"
 args = default_args(scenario_name=scen, dynamics_type=dyn, num_agents=n, num_landmarks=n, world_size=max(3, n // 2),
                     episode_length=50, collaborative=False)

@@ -22,11 +22,12 @@ CASES = [
     dict(scenario_name="nav_metered_one_goal_graph_rotate_tube_july", dynamics_type="air_taxi", num_agents=64,
          num_landmarks=64, world_size=12, episode_length=3, goal_rew=30, collaborative=False),
 ]
-for kern in ("auto", "world", "tile"):
-    if kern == "auto":
-        os.environ.pop("GMPE_KERNEL", None)
-    else:
-        os.environ["GMPE_KERNEL"] = kern
+from gmpe_b200 import config as _config  # noqa: E402
+
+CASES.append(dict(scenario_name="three_phase_graph", dynamics_type="air_taxi", world_size=3, num_agents=5, num_landmarks=5,
+                  episode_length=4, goal_rew=20, collaborative=False))
+for kern in ("auto", "tile"):
+    _config.FORCE_TILE_DEFAULT = kern == "tile"  # the lane-per-agent kernel where gmpe_create picks it / the tile kernel forced
     for kw in CASES:
         for prec in ("fp32", "fp64"):
             B = 77 if kw.get("num_agents", 3) < 64 else 5
@@ -41,6 +42,7 @@ for kern in ("auto", "world", "tile"):
             m[::3] = 1
             eng.reset(env_mask=m.cuda())
             eng.step_range(a, B // 5, B // 2)
+            ei, ea = eng.gnn_flat_edges()  # scan + gather kernels (gmpe_flat.cuh)
             torch.cuda.synchronize()
             print(kern, kw["scenario_name"][:14], kw.get("num_agents", 3), prec, eng.kernel_name, float(eng.out["reward"].sum()))
             eng.close()
