@@ -215,12 +215,15 @@ class BatchedGraphMPE:
         (gnn_new.py:492-500 -> process_adj :328-358 on the (B*N, E, E) stack): ``edge_index`` int64
         (2, nnz) with node ids ``(world * N + agent) * E + entity`` in (graph, row, col) order and
         ``edge_attr`` (nnz, 1).  Built on the device from the step kernel's per-world list (scan +
-        gather); reading ``nnz`` is the one host synchronisation, as in ``Tensor.nonzero``.
+        gather); reading ``nnz`` is the host synchronisation, as in ``Tensor.nonzero`` (with
+        ``capacity=None`` the buffers are sized from the sum of the per-world counts first).
         Needs ``gnn_edges=True``.  The results are views of buffers the engine reuses."""
         if "gnn_edge_index" not in self.out:
             raise abi.GmpeError("gnn_flat_edges needs the consumer-side edge list: make_config(..., gnn_edges=True)")
-        cap_max = self.B * self.N * self.layout.edge_cap
-        capacity = cap_max if capacity is None else int(capacity)
+        src = self.out if out_struct is None else getattr(out_struct, "_keepalive", self.out)
+        if capacity is None:  # exact: the per-world counts are on the device already (one small reduction + read)
+            capacity = max(1, int(src["gnn_num_edges"].sum(dtype=torch.int64).item()) * self.N)
+        capacity = int(capacity)
         buf = getattr(self, "_flat", None)
         if buf is None or buf[0].shape[1] < capacity:
             with torch.cuda.device(self.device):
