@@ -158,4 +158,4 @@ def test_fp32_teacher_forced_per_step(case):
     cs = fp32_census.run_teacher_forced(cfg64, cfg32, acts, tol=1e-5, label=case)
     print("fp32 census", case, cs.as_dict())
     assert cs.int_mismatch <= _int_mismatch_bound(cfg64, cs.world_steps), cs.as_dict()
-    assert cs.tie_excused + cs.sep_excused + cs.trunc_excused <= 1 + int(1e-4 * cs.world_steps), cs.as_dict()
+    assert cs.tie_excused + cs.sep_excused + cs.trunc_excused + cs.phase_excused + cs.obst_excused <= 1 + int(1e-4 * cs.world_steps), cs.as_dict()
