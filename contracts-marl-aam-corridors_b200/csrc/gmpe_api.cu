@@ -431,7 +431,7 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
     h->threads = GMPE_LB_THREADS;
     if (const char* t = tuning_env("GMPE_THREADS")) {  // tuning knob (tools/sweep.py); must not exceed the launch bound
       int v = atoi(t);
-      if (v >= 32 && v <= GMPE_LB_THREADS && v % 32 == 0) h->threads = v;
+      if (v >= 32 && v <= GMPE_LB_THREADS && v % 32 == 0 && v >= cfg->num_agents) h->threads = v;  // phase A needs a thread per agent of a world
     }
     plan_tiles(h->cfg, h->threads, &h->wpb, &h->num_tiles);
     h->stage_graph = pick_stage_graph(h->cfg, h->wpb);
