@@ -19,7 +19,7 @@ SCEN_JULY_TUBE, SCEN_NAV_GRAPH, SCEN_THREE_PHASE, SCEN_TWO_PHASE, SCEN_CORRIDOR_
 ROT_INV_SCENARIOS = (SCEN_THREE_PHASE, SCEN_TWO_PHASE, SCEN_CORRIDOR_ROT_INV)
 # the lane-per-agent kernel is instantiated for these world sizes (README.md:88 and
 # eval_scripts/commands_test_run.txt:7,30 of the reference: 3, 5 and 10 agents)
-ROT_INV_AGENT_COUNTS = tuple(range(2, 11))
+ROT_INV_AGENT_COUNTS = tuple(range(2, 17))  # gmpe_coop_table.h: COOP_MAX_AGENTS_ROT_INV
 DYN_DOUBLE_INTEGRATOR, DYN_UNICYCLE, DYN_AIR_TAXI = 0, 1, 2
 PHYS_KINEMATIC, PHYS_FORCE = 0, 1
 F32, F64 = 0, 1

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "libgmpe_b200.so")
 # one translation unit for the host side + tile kernel, one per precision for
 # the lane-per-agent kernel instantiations: compiled in parallel, linked into one library
-SOURCES = ["gmpe_api.cu", "gmpe_coop_f32.cu", "gmpe_coop_f64.cu"]
+SOURCES = ["gmpe_api.cu", "gmpe_coop_f32.cu", "gmpe_coop_f64.cu", "gmpe_coop_wide_f32.cu", "gmpe_coop_wide_f64.cu"]
 DEPS = SOURCES + ["gmpe_step.cuh", "gmpe_place.cuh", "gmpe_coop.cuh", "gmpe_device.cuh", "gmpe_flat.cuh", "gmpe_coop_table.h",
                   os.path.join("..", "..", "include", "gmpe.h")]
 

@@ -144,6 +144,7 @@ struct gmpe_ctx {
   int sm_count;
   int threads;
   int wpb;
+  int coop_warps;
   int num_tiles;
   int grid;
   size_t smem_bytes;
@@ -218,9 +219,9 @@ static const char* validate(const GmpeConfig& c) {
   if (c.num_landmarks < c.num_agents) return "num_landmarks must be >= num_agents";
   if (c.num_obstacles < 0 || c.num_walls < 0) return "negative entity count";
   if (c.num_agents + c.num_landmarks + c.num_obstacles + c.num_walls > GMPE_MAX_ENTITIES) return "too many entities";
-  if (rot_inv(c) && !(c.num_agents >= COOP_MIN_AGENTS && c.num_agents <= COOP_MAX_AGENTS &&
+  if (rot_inv(c) && !(c.num_agents >= COOP_MIN_AGENTS && c.num_agents <= COOP_MAX_AGENTS_ROT_INV &&
                       c.num_landmarks == c.num_agents && c.num_obstacles == 0 && c.num_walls == 0 && c.physics == GMPE_PHYS_KINEMATIC))
-    return "the rot-inv scenarios are served for 2 <= num_agents == num_landmarks <= 10 without obstacles / walls, kinematic step";
+    return "the rot-inv scenarios are served for 2 <= num_agents == num_landmarks <= 16 without obstacles / walls, kinematic step";
   if (c.scenario == GMPE_SCEN_JULY_TUBE && (c.num_obstacles || c.num_walls))
     return "july tube scenario supports num_obstacles == num_walls == 0 only (the reference graph builder raises, SURVEY G7)";
   if (c.physics == GMPE_PHYS_FORCE && c.dynamics != GMPE_DYN_DOUBLE_INTEGRATOR) return "force physics needs double_integrator state";
@@ -290,7 +291,7 @@ static int pick_stage_graph(const GmpeConfig& c, int wpb) {
 // the choice (A/B timing, and the tests that keep both mappings pinned to the oracle).
 enum { KERNEL_TILE = 0, KERNEL_COOP = 2 };
 static int pick_kernel(const GmpeConfig& c) {
-  if (rot_inv(c)) return KERNEL_COOP;  // only the lane-per-agent kernel serves that family (2 <= N = L <= 10)
+  if (rot_inv(c)) return KERNEL_COOP;  // only the lane-per-agent kernel serves that family (2 <= N = L <= 16)
   const bool small = c.num_agents >= COOP_MIN_AGENTS && c.num_agents <= COOP_MAX_AGENTS && c.num_landmarks == c.num_agents &&
                      c.num_obstacles == 0 && c.num_walls == 0;
   if (!small) return KERNEL_TILE;
@@ -415,12 +416,13 @@ int gmpe_create(const GmpeConfig* cfg, int device, gmpe_handle* out) {
   int units = 0;  // CTAs needed to cover the batch once
   if (h->small == KERNEL_COOP) {
     // one lane per agent, floor(32 / N) worlds per warp, warps independent: gmpe_coop.cuh
-    h->threads = 32 * GMPE_COOP_WARPS;
-    h->wpb = GMPE_COOP_WARPS * (32 / cfg->num_agents);
-    h->num_tiles = (cfg->num_worlds + h->wpb - 1) / h->wpb;
     h->stage_graph = 0;
-    const bool found = f64 ? coop_lookup_f64(cfg->scenario, cfg->num_agents, &h->fn, &h->smem_bytes)
-                           : coop_lookup_f32(cfg->scenario, cfg->num_agents, &h->fn, &h->smem_bytes);
+    h->coop_warps = 0;  // warps per CTA of the instantiation (4; fewer for the widest worlds, whose slabs are large)
+    const bool found = f64 ? coop_lookup_f64(cfg->scenario, cfg->num_agents, &h->fn, &h->smem_bytes, &h->coop_warps)
+                           : coop_lookup_f32(cfg->scenario, cfg->num_agents, &h->fn, &h->smem_bytes, &h->coop_warps);
+    h->threads = 32 * h->coop_warps;
+    h->wpb = h->coop_warps * (32 / cfg->num_agents);
+    h->num_tiles = found ? (cfg->num_worlds + h->wpb - 1) / h->wpb : 0;
     if (!found) {
       cudaSetDevice(prev);
       const int code = fail(nullptr, GMPE_E_INVALID, "no lane-per-agent kernel for this scenario / num_agents");
@@ -608,10 +610,10 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   }
   p.stage_graph = h->stage_graph;
   memcpy(p.act_tab_c, h->act_tab_host, sizeof(p.act_tab_c));
-  if (h->small == KERNEL_COOP) {  // round structure of the persistent grid (num_tiles counts CTAs of GMPE_COOP_WARPS warps)
+  if (h->small == KERNEL_COOP) {  // round structure of the persistent grid (num_tiles counts CTAs of coop_warps warps)
     const int wpw = 32 / c.num_agents;
     p.coop_groups = (int)((p.c.num_worlds + wpw - 1) / wpw);
-    p.coop_full_rounds = p.coop_groups / (grid * GMPE_COOP_WARPS);
+    p.coop_full_rounds = p.coop_groups / (grid * h->coop_warps);
   }
   const int N = c.num_agents, L = c.num_landmarks, O = c.num_obstacles, W = c.num_walls;
   p.E = N + L + O + W;

@@ -97,8 +97,12 @@ struct CoopTraits {
   // resident CTAs still fit in shared memory, else they share one and B waits for A to drain.
   // resident CTAs asked of the compiler: the register budget has to grow with the per-lane
   // world image (positions, goals, velocities and two distance rows of 2N entries)
-  static constexpr int MINBLOCKS = N > 5 ? (R == 4 ? GMPE_COOP_MINBLOCKS_N6 : 1) : (N > 3 ? (R == 4 ? GMPE_COOP_MINBLOCKS_N4 : 2) : (R == 4 ? (ROT_INV ? GMPE_COOP_MINBLOCKS_TP : (SCEN == GMPE_SCEN_NAV_GRAPH ? GMPE_COOP_MINBLOCKS_NAV : GMPE_COOP_MINBLOCKS_F32)) : GMPE_COOP_MINBLOCKS_F64));
-  static constexpr bool SPLIT = GMPE_COOP_BULK_STORE && (up16(ROUND_A + ROUND_B) + 0) * GMPE_COOP_WARPS * MINBLOCKS <= 220 * 1024;
+  // warps per CTA: GMPE_COOP_WARPS unless the slabs of that many warps no longer fit in one SM's
+  // shared memory (wide rot-inv worlds, 11 <= N <= 16: up to 78 KB per warp in fp64)
+  static constexpr int SLAB_MIN = up16(ROUND_A > ROUND_B ? ROUND_A : ROUND_B);
+  static constexpr int WARPS = SLAB_MIN * GMPE_COOP_WARPS <= 220 * 1024 ? GMPE_COOP_WARPS : (SLAB_MIN * 2 <= 220 * 1024 ? 2 : 1);
+  static constexpr int MINBLOCKS = N > 10 ? 1 : N > 5 ? (R == 4 ? GMPE_COOP_MINBLOCKS_N6 : 1) : (N > 3 ? (R == 4 ? GMPE_COOP_MINBLOCKS_N4 : 2) : (R == 4 ? (ROT_INV ? GMPE_COOP_MINBLOCKS_TP : (SCEN == GMPE_SCEN_NAV_GRAPH ? GMPE_COOP_MINBLOCKS_NAV : GMPE_COOP_MINBLOCKS_F32)) : GMPE_COOP_MINBLOCKS_F64));
+  static constexpr bool SPLIT = GMPE_COOP_BULK_STORE && (up16(ROUND_A + ROUND_B) + 0) * WARPS * MINBLOCKS <= 220 * 1024;
   static constexpr int B_OFF = SPLIT ? ROUND_A : 0;
   static constexpr int SLAB_BYTES = SPLIT ? up16(ROUND_A + ROUND_B) : up16(ROUND_A > ROUND_B ? ROUND_A : ROUND_B);
 };
@@ -150,7 +154,7 @@ template <typename Real>
 __device__ __forceinline__ Real shfl_(Real v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 template <typename Real, int SCEN, int N>
-__global__ void __launch_bounds__(32 * GMPE_COOP_WARPS, CoopTraits<Real, SCEN, N>::MINBLOCKS)
+__global__ void __launch_bounds__(32 * CoopTraits<Real, SCEN, N>::WARPS, CoopTraits<Real, SCEN, N>::MINBLOCKS)
 gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
   using V2 = typename RT<Real>::V2;
   using V4 = typename RT<Real>::V4;
@@ -208,10 +212,10 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
   // together at warp granularity.
   bool ei_pattern = false;  // the round-B region holds the dense edge_index pattern (see the edge emission)
   const int num_groups = p.coop_groups, full_rounds = p.coop_full_rounds;
-  const int grid_warps = (int)gridDim.x * GMPE_COOP_WARPS;
+  const int grid_warps = (int)gridDim.x * T::WARPS;
   for (int rnd = 0; rnd <= full_rounds; ++rnd) {
     const int slot = (GMPE_COOP_TRANSPOSE_TAIL && rnd == full_rounds) ? warp * (int)gridDim.x + (int)blockIdx.x
-                                                                      : (int)blockIdx.x * GMPE_COOP_WARPS + warp;
+                                                                      : (int)blockIdx.x * T::WARPS + warp;
     const int grp = rnd * grid_warps + slot;
     if (grp >= num_groups) break;
     const int64_t wbase = (int64_t)grp * WPW;

@@ -42,7 +42,7 @@ extern "C" {
 #define GMPE_SCEN_NAV_GRAPH 1 /* navigation_graph-class, defined-by-build */
 #define GMPE_SCEN_THREE_PHASE 2 /* three_phase_graph.py: rotation-invariant fp32 features, 15-d obs,
                                    7-d nodes, exit gate, random tube length;
-                                   served for 2 <= N = L <= 10 (the reference runs it with 3, 5 and 10
+                                   served for 2 <= N = L <= 16 (the reference runs it with 3, 5 and 10
                                    agents: README.md:88, eval_scripts/commands_test_run.txt:7,30), O = W = 0 */
 #define GMPE_SCEN_TWO_PHASE 3 /* two_phase_graph.py (eval_scripts/commands_test_run.txt:14): the same family;
                                  the goal is the tube exit -- an agent is done when it leaves through the

@@ -427,10 +427,26 @@ MULTIAGENT_FORCE_TRACES = (
     ("multiagent_force_n6_o4_w4_s53.npz", dict(seed=53, T=150, num_agents=6, num_obstacles=4)),
 )
 
+# the rot-inv family beyond the shapes of the reference's README: 11 <= N = L <= 16 (E = 2N <= 32), served by
+# the wide instantiations of the lane-per-agent kernel (csrc/gmpe_coop_wide_f32.cu / _f64.cu)
+ROT_INV_WIDE_TRACES = (
+    ("three_phase_n12_pursuit_s26.npz", dict(seed=26, T=120, policy="pursuit", scenario_name="three_phase_graph",
+                                             num_agents=12, num_landmarks=12, world_size=5)),
+    ("two_phase_n13_pursuit_s35.npz", dict(seed=35, T=100, policy="pursuit", scenario_name="two_phase_graph",
+                                           num_agents=13, num_landmarks=13, world_size=5)),
+    ("corridor_rot_inv_n16_pursuit_s44.npz", dict(seed=44, T=80, policy="pursuit", episodes=2,
+                                                  scenario_name="nav_graph_metered_single_corridor_rot_inv",
+                                                  num_agents=16, num_landmarks=16, world_size=6)),
+)
+
 
 def main():
     install_shims()
     g = lambda name: os.path.join(HERE, name)
+    if "--rot-inv-wide" in sys.argv:  # only the wide rot-inv traces (11 <= N <= 16) added late in round 2
+        for name, kw in ROT_INV_WIDE_TRACES:
+            run_july_trace(g(name), **kw)
+        return
     if "--multiagent-force" in sys.argv:  # only the traces added in round 2
         for name, kw in MULTIAGENT_FORCE_TRACES:
             run_multiagent_force_trace(g(name), **kw)
@@ -479,6 +495,8 @@ def main():
                    scenario_name="nav_graph_metered_single_corridor_rot_inv")
     run_july_trace(g("corridor_rot_inv_n3_pursuit_s42_ep2.npz"), seed=42, T=110, policy="pursuit", eps=0.3, episodes=2,
                    scenario_name="nav_graph_metered_single_corridor_rot_inv")
+    for name, kw in ROT_INV_WIDE_TRACES:
+        run_july_trace(g(name), **kw)
     # stage-1 force physics: the live classic-MPE World.step
     run_classic_trace(g("classic_spread_n3_s11.npz"), seed=11, T=120)
     run_classic_trace(g("classic_spread_n6_s12.npz"), seed=12, T=80, num_agents=6, num_landmarks=6)

@@ -64,6 +64,18 @@ CASES = {
                                           collaborative=False), B=300, T=30),
     "corridor_rot_inv_n3": dict(args=dict(scenario_name="nav_graph_metered_single_corridor_rot_inv", dynamics_type="air_taxi",
                                           world_size=3, episode_length=25, goal_rew=30, collaborative=False), B=1000, T=30),
+    # wide worlds of the rot-inv family (11 <= N <= 16: gmpe_coop_wide_f32.cu / _f64.cu), Philox placement + auto-resets
+    "three_phase_n12": dict(args=dict(scenario_name="three_phase_graph", dynamics_type="air_taxi", world_size=5, num_agents=12,
+                                      num_landmarks=12, episode_length=10, goal_rew=20, collision_rew=20, collaborative=False),
+                            B=150, T=25),
+    "two_phase_n14": dict(args=dict(scenario_name="two_phase_graph", dynamics_type="air_taxi", world_size=5, num_agents=14,
+                                    num_landmarks=14, episode_length=10, goal_rew=20, collaborative=True), B=101, T=25),
+    "corridor_rot_inv_n16": dict(args=dict(scenario_name="nav_graph_metered_single_corridor_rot_inv", dynamics_type="air_taxi",
+                                           world_size=6, num_agents=16, num_landmarks=16, episode_length=12, goal_rew=30,
+                                           collaborative=False), B=97, T=25),
+    "three_phase_n11_unicycle": dict(args=dict(scenario_name="three_phase_graph", dynamics_type="unicycle_vehicle", world_size=5,
+                                               num_agents=11, num_landmarks=11, episode_length=9, goal_rew=30,
+                                               collaborative=False), B=64, T=20),
     "july_di_kinematic": dict(args=dict(scenario_name="nav_metered_one_goal_graph_rotate_tube_july",
                                         dynamics_type="double_integrator", world_size=3, episode_length=12,
                                         goal_rew=30, collaborative=False, total_actions=9), B=200, T=20),
