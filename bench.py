@@ -541,7 +541,7 @@ def run_ours(opts):
         "wall_s_timed_region": t_wall,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel "
-                                                           "and workload, profiles/r2_ncu_full_*; not re-measured by this run)",
+                                                           "and workload, profiles/r2x_ncu_full_*; not re-measured by this run)",
                      "peak_source": peak_src, "kernel": kernel_name + "<float>",
                      "algorithmic_bytes_per_launch": abytes, "kernel_ms": kernel_ms,
                      "frac_survey_formula": sbytes / (kernel_ms * 1e-3) / 1e9 / peak,
