@@ -81,6 +81,13 @@ def test_invalid_config_is_rejected_with_error_code_not_exception():
     assert b"num_agents" in lib.gmpe_last_error(None)
     assert lib.gmpe_destroy(None) == abi.E_NULL
     assert lib.gmpe_step(None, None, None, None, None, None) == abi.E_NULL
+    # rot-inv family beyond N = 16: refused by the library itself with the reason, not only by make_config
+    cfg = make_config(default_args(scenario_name="two_phase_graph", dynamics_type="air_taxi", num_agents=16, num_landmarks=16), 4)
+    assert lib.gmpe_layout(C.byref(cfg), C.byref(lay)) == abi.OK
+    cfg.num_agents = cfg.num_landmarks = 17
+    assert lib.gmpe_layout(C.byref(cfg), C.byref(lay)) == abi.E_INVALID
+    assert lib.gmpe_create(C.byref(cfg), 0, C.byref(h)) == abi.E_INVALID
+    assert b"<= 16" in lib.gmpe_last_error(None)
 
 
 def test_missing_library_fails_loudly(tmp_path):

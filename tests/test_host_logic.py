@@ -39,6 +39,10 @@ def test_config_rejects_what_the_reference_cannot_run():
         make_config(default_args(num_agents=5, num_landmarks=3), 2)
     with pytest.raises(NotImplementedError):
         make_config(default_args(use_safety_filter=True), 2)
+    # the rot-inv family is served for 2 <= N = L <= 16 (a graph row of E = 2N entities in one 32-bit lane mask)
+    make_config(default_args(scenario_name="three_phase_graph", dynamics_type="air_taxi", num_agents=16, num_landmarks=16), 2)
+    with pytest.raises(ValueError, match="rot-inv"):
+        make_config(default_args(scenario_name="three_phase_graph", dynamics_type="air_taxi", num_agents=17, num_landmarks=17), 2)
 
 
 def test_actions_to_index_mirrors_set_action_front_half():
