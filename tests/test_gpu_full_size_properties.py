@@ -101,6 +101,29 @@ def test_results_do_not_depend_on_the_sharding(args):
     shard.close()
 
 
+WIDE = dict(scenario_name="nav_graph_metered_single_corridor_rot_inv", dynamics_type="air_taxi", num_agents=16, num_landmarks=16,
+            world_size=6, episode_length=6, goal_rew=30, collaborative=False)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_wide_rot_inv_worlds_do_not_depend_on_the_sharding(precision):
+    """The wide lane-per-agent instantiations (N = 16: two worlds per warp, 4 warps per CTA in fp32, 2 in fp64):
+    an odd batch (partial last group, transposed tail) and a shard of it agree bit for bit through auto-resets."""
+    B, B0, Bs, T = 2051, 1025, 513, 14
+    cfg, big = _run(WIDE, B, T, precision=precision)
+    cfg_s, shard = _run(WIDE, Bs, T, world_offset=B0, precision=precision)
+    for t in range(T):
+        ob = big.step(_actions(cfg, t, 0, B))
+        osh = shard.step(_actions(cfg, t, B0, Bs))
+        for k in ("obs", "node_obs", "adj", "reward", "done", "edge_index", "edge_attr", "num_edges", "gnn_edge_index", "gnn_num_edges"):
+            a, b = ob[k][B0:B0 + Bs], osh[k]
+            assert torch.equal(a, b) or torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)), (t, k)
+    for k in ("agent_state", "agent_flags", "agent_cnt", "agent_ext", "world_f", "landmarks"):
+        assert torch.equal(big.state[k][B0:B0 + Bs], shard.state[k]), k
+    big.close()
+    shard.close()
+
+
 def test_sampled_worlds_of_the_full_batch_match_the_oracle():
     """fp64 instantiation at 65,536 worlds, free-running with auto-resets; 512 worlds spread
     over the batch are replayed by the CPU oracle with their global ids and compared exactly
