@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # error codes
 OK, E_INVALID, E_CUDA, E_NULL = 0, -1, -2, -3
@@ -55,6 +55,11 @@ INFO_KEYS = (
     "Time_taken", "Time_mean", "Time_stddev", "Time_mean_by_stddev", "Conformance",
     "Delta_spacing", "Spacing_violations", "Min_time_to_goal",
 )
+#: info dict of the rot-inv family (three_phase_graph.py:788-811, two_phase_graph.py:786-809,
+#: nav_graph_metered_single_corridor_rot_inv.py:822-845): 'Phase_reached' sits before 'Min_time_to_goal';
+#: its value is GmpeStepOut.phase_reached, not a column of the 16-wide info row
+INFO_KEYS_ROT_INV = INFO_KEYS[:-1] + ("Phase_reached",) + INFO_KEYS[-1:]
+
 
 
 class GmpeConfig(C.Structure):
@@ -105,7 +110,7 @@ class GmpeState(C.Structure):
 class GmpeStepOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "obs", "node_obs", "adj", "reward", "done", "info", "edge_index", "edge_attr", "num_edges",
-        "gnn_edge_index", "gnn_edge_attr", "gnn_num_edges", "indiv_reward", "mask", "active_mask")]
+        "gnn_edge_index", "gnn_edge_attr", "gnn_num_edges", "indiv_reward", "mask", "active_mask", "phase_reached")]
 
 
 class GmpeStepInject(C.Structure):

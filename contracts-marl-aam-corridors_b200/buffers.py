@@ -14,7 +14,7 @@ from . import abi
 STATE_FIELDS = ("agent_state", "agent_aux", "agent_flags", "agent_cnt", "world_f", "world_i",
                 "landmarks", "obstacles", "walls", "agent_ext")
 OUT_FIELDS = ("obs", "node_obs", "adj", "reward", "done", "info", "edge_index", "edge_attr",
-              "num_edges", "gnn_edge_index", "gnn_edge_attr", "gnn_num_edges", "indiv_reward")
+              "num_edges", "gnn_edge_index", "gnn_edge_attr", "gnn_num_edges", "indiv_reward", "phase_reached")
 #: optional float32 outputs (runner masks); only requested by DeviceGraphRollout
 MASK_FIELDS = ("mask", "active_mask")
 
@@ -50,6 +50,7 @@ def shapes(cfg: abi.GmpeConfig) -> dict:
         "indiv_reward": ((B, N), "real"),
         "mask": ((B, N), "f32"),
         "active_mask": ((B, N), "f32"),
+        "phase_reached": ((B, N), "u8"),
     }
 
 
@@ -57,6 +58,8 @@ def wanted_outputs(cfg: abi.GmpeConfig) -> tuple:
     names = ["obs", "node_obs", "adj", "reward", "done"]
     if cfg.flags & abi.FLAG_INFO:
         names += ["indiv_reward", "info"]
+        if cfg.scenario in abi.ROT_INV_SCENARIOS:  # info['Phase_reached'] (three_phase_graph.py:806)
+            names += ["phase_reached"]
     if cfg.flags & abi.FLAG_ENV_EDGES:
         names += ["edge_index", "edge_attr", "num_edges"]
     if cfg.flags & abi.FLAG_GNN_EDGES:

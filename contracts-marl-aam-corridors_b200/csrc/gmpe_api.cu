@@ -355,6 +355,7 @@ static void rebase_out(GmpeStepOut& o, const GmpeConfig& c, int64_t b0, int64_t 
   shift_bytes(o.indiv_reward, b0 * N * R);
   shift(o.mask, b0 * N);
   shift(o.active_mask, b0 * N);
+  shift(o.phase_reached, b0 * N);
 }
 
 extern "C" {
@@ -711,10 +712,11 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
   const int64_t B = c.num_worlds, N = c.num_agents, E = N + c.num_landmarks + c.num_obstacles + c.num_walls, cap = E * (E - 1);
   const int64_t R = c.precision == GMPE_F64 ? 8 : 4, F = obs_dim_of(c), ND = node_dim_of(c);
   const int64_t act_bpw = action_kind == 0 ? N * 4 : N * (int64_t)c.total_actions * action_kind;  // bytes per world
-  // GmpeStepOut is fifteen pointers in declaration order: bytes per world of each
-  const int64_t bpw[15] = {N * F * R, N * E * ND * R, E * E * R, N * R, N, N * GMPE_INFO_K * R, 2 * cap * 4, cap * R, 4,
-                           2 * cap * 4, cap * R, 4, N * R, N * 4, N * 4};
-  static_assert(sizeof(GmpeStepOut) == 15 * sizeof(void*), "GmpeStepOut layout");
+  // GmpeStepOut is sixteen pointers in declaration order: bytes per world of each
+  constexpr int NOUT = 16;
+  const int64_t bpw[NOUT] = {N * F * R, N * E * ND * R, E * E * R, N * R, N, N * GMPE_INFO_K * R, 2 * cap * 4, cap * R, 4,
+                             2 * cap * 4, cap * R, 4, N * R, N * 4, N * 4, N};
+  static_assert(sizeof(GmpeStepOut) == NOUT * sizeof(void*), "GmpeStepOut layout");
   void* const* dptr = reinterpret_cast<void* const*>(dev_out);
   void* const* hptr = reinterpret_cast<void* const*>(host_out);
   int prev = 0;
@@ -791,7 +793,7 @@ int gmpe_step_host(gmpe_handle h, const GmpeState* st, const void* actions_host,
   if (e == cudaSuccess && rc == GMPE_OK) {
     e = cudaEventRecord(h->ev[1], main_s);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_out, h->ev[1], 0);
-    for (int f = 0; f < 15 && e == cudaSuccess; ++f)
+    for (int f = 0; f < NOUT && e == cudaSuccess; ++f)
       if (dptr[f] && hptr[f])
         e = cudaMemcpyAsync(hptr[f], dptr[f], (size_t)(B * bpw[f]), cudaMemcpyDeviceToHost, h->s_out);
 #ifdef GMPE_EXPERIMENTS

@@ -53,8 +53,8 @@ class BatchedGraphMPE:
             self.out_slabs = offs
             self.out = {n: self.out_arena[o:o + nb].view(kinds[sh[n][1]]).view(sh[n][0]) for n, (o, nb) in offs.items()}
             #: bytes from the arena start that hold what MultiAgentGraphEnv.step returns
-            #: (obs, node_obs, adj, reward, done[, indiv_reward, info]); edges come after
-            host_names = [n for n in names if n in ("obs", "node_obs", "adj", "reward", "done", "indiv_reward", "info")]
+            #: (obs, node_obs, adj, reward, done[, indiv_reward, info[, phase_reached]]); edges come after
+            host_names = [n for n in names if n in ("obs", "node_obs", "adj", "reward", "done", "indiv_reward", "info", "phase_reached")]
             self.host_prefix_bytes = max(offs[n][0] + offs[n][1] for n in host_names)
             self.action_idx = torch.zeros((self.B, self.N), dtype=torch.int32, device=self.device)
         self._st = buffers.make_struct(abi.GmpeState, self.state)

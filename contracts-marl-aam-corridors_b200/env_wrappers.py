@@ -78,14 +78,15 @@ class ShareVecEnv(ABC):  # env_wrappers.py:29-140
 
 
 class _AgentInfo:
-    """dict-like view of one (env, agent) row of the info tensor."""
-    __slots__ = ("_row", "_rew")
+    """dict-like view of one (env, agent) row of the info tensor (``phase``: the rot-inv family's
+    'Phase_reached' entry, three_phase_graph.py:806; None for the scenarios without that key)."""
+    __slots__ = ("_row", "_rew", "_phase")
 
-    def __init__(self, row, rew):
-        self._row, self._rew = row, rew
+    def __init__(self, row, rew, phase=None):
+        self._row, self._rew, self._phase = row, rew, phase
 
     def keys(self):
-        return ("individual_reward",) + abi.INFO_KEYS
+        return ("individual_reward",) + (abi.INFO_KEYS if self._phase is None else abi.INFO_KEYS_ROT_INV)
 
     def __contains__(self, k):
         return k in self.keys()
@@ -93,6 +94,8 @@ class _AgentInfo:
     def __getitem__(self, k):
         if k == "individual_reward":
             return self._rew
+        if k == "Phase_reached" and self._phase is not None:
+            return self._phase
         return self._row[abi.INFO_KEYS.index(k)]
 
     def get(self, k, default=None):
@@ -121,13 +124,19 @@ class LazyInfos:
     again (the device rows are overwritten); a later access raises instead of returning the
     wrong step's values."""
 
-    def __init__(self, info: np.ndarray = None, indiv_reward: np.ndarray = None, fetch=None):
-        self._info, self._rew, self._fetch = info, indiv_reward, fetch
+    def __init__(self, info: np.ndarray = None, indiv_reward: np.ndarray = None, fetch=None, phase_reached: np.ndarray = None):
+        self._info, self._rew, self._fetch, self._phase = info, indiv_reward, fetch, phase_reached
 
     def _load(self):
         if self._info is None:
-            self._info, self._rew = self._fetch()
+            self._info, self._rew, self._phase = self._fetch()
             self._fetch = None
+
+    @property
+    def phase_reached(self):
+        """(B, N) uint8 'Phase_reached' of the rot-inv family, None for the other scenarios."""
+        self._load()
+        return self._phase
 
     @property
     def info(self) -> np.ndarray:
@@ -147,7 +156,8 @@ class LazyInfos:
             return [self[i] for i in range(*e.indices(len(self)))]
         if e < 0:
             e += len(self)
-        return [_AgentInfo(self.info[e, a], self.rew[e, a]) for a in range(self.info.shape[1])]
+        ph = self.phase_reached
+        return [_AgentInfo(self.info[e, a], self.rew[e, a], None if ph is None else ph[e, a]) for a in range(self.info.shape[1])]
 
     def __iter__(self):
         return (self[e] for e in range(len(self)))
@@ -222,8 +232,8 @@ class _BatchedVecEnv(ShareVecEnv):
         #: rewritten before the copy has executed (with output="torch" nothing else makes the host wait)
         self._h2d_done = torch.cuda.Event()
         self._h2d_pending = False
-        self._host_names = [n for n in ("obs", "node_obs", "adj", "reward", "done", "indiv_reward", "info")
-                            if n in self.engine.out_slabs and not (self._lazy_info and n in ("indiv_reward", "info"))]
+        self._host_names = [n for n in ("obs", "node_obs", "adj", "reward", "done", "indiv_reward", "info", "phase_reached")
+                            if n in self.engine.out_slabs and not (self._lazy_info and n in ("indiv_reward", "info", "phase_reached"))]
         self._host_t = [self._host_tensors(a) for a in self._arena]
         #: numpy views of the two pinned arenas, built once (a step hands one of them out)
         self._views = {a.data_ptr(): self._host_views(a) for a in self._arena}
@@ -237,7 +247,7 @@ class _BatchedVecEnv(ShareVecEnv):
         eng = self.engine
         real = np.float64 if self.cfg.precision == abi.F64 else np.float32
         kinds = {"obs": real, "node_obs": real, "adj": real, "reward": real, "indiv_reward": real, "info": real,
-                 "done": np.uint8}
+                 "done": np.uint8, "phase_reached": np.uint8}
         out = {}
         for n, (off, nb) in eng.out_slabs.items():
             if n in kinds and off + nb <= np_arena.size:
@@ -308,7 +318,7 @@ class _BatchedVecEnv(ShareVecEnv):
             torch.cuda.current_stream(eng.device).synchronize()
             self.d2h_bytes_last += hi - lo
             v = self._views[arena.data_ptr()]
-            return v["info"], v["indiv_reward"]
+            return v["info"], v["indiv_reward"], v.get("phase_reached")
         return fetch
 
     def _pack_obs(self, o):
@@ -380,13 +390,15 @@ class _BatchedVecEnv(ShareVecEnv):
             infos = None
             if "info" in o:
                 infos = {"info": o["info"], "individual_reward": o["indiv_reward"]}
+                if "phase_reached" in o:
+                    infos["phase_reached"] = o["phase_reached"]
         else:
             rews = o["reward"][..., None] if collab else o["reward"]  # [[sum]]*N -> (B,N,1), environment.py:1059
             dones = o["done"].view(np.bool_)
             if self._lazy_info:
                 infos = LazyInfos(fetch=self._info_fetcher(self._last_arena))
             else:
-                infos = LazyInfos(o["info"], o["indiv_reward"]) if "info" in o else tuple([{}] * 0)
+                infos = LazyInfos(o["info"], o["indiv_reward"], phase_reached=o.get("phase_reached")) if "info" in o else tuple([{}] * 0)
         if self.returns_reset_count:
             # env_wrappers.py:925-936: reset_count = 1 when any env auto-reset this step
             if self.output == "torch":

@@ -228,8 +228,12 @@ class Scenario(BaseScenario):
         return np.array([agent.global_id])
 
     def info_callback(self, agent: Agent, world: World) -> dict:
-        row = world._outputs()["info"][0, agent.id]
-        return {k: row[j] for j, k in enumerate(abi.INFO_KEYS)}
+        o = world._outputs()
+        row = o["info"][0, agent.id]
+        d = {k: row[j] for j, k in enumerate(abi.INFO_KEYS)}
+        if "phase_reached" in o:  # rot-inv family (three_phase_graph.py:806): same key order as the reference dict
+            d = {k: (int(o["phase_reached"][0, agent.id]) if k == "Phase_reached" else d[k]) for k in abi.INFO_KEYS_ROT_INV}
+        return d
 
     def done(self, agent: Agent, world: World) -> bool:
         return bool(world._outputs()["done"][0, agent.id])

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GMPE_ABI_VERSION 12
+#define GMPE_ABI_VERSION 13
 
 /* error codes */
 #define GMPE_OK 0
@@ -235,6 +235,11 @@ typedef struct GmpeStepOut {
   float* active_mask;      /* f32 [B][N] ... active_masks: like mask, but 1 for every agent of a world
                                           whose agents are all done (graph_mpe_runner.py:403-405); both
                                           are float32 like the reference buffer, written by gmpe_step only */
+  uint8_t* phase_reached;  /* u8 [B][N] rot-inv family only: info['Phase_reached'] = Scenario.phase_reached[agent.id]
+                                          at info_callback time (three_phase_graph.py:806, two_phase_graph.py:804,
+                                          nav_graph_metered_single_corridor_rot_inv.py:840); like the info rows it keeps
+                                          the terminal step's value when the world auto-resets; NULL = not wanted;
+                                          written by gmpe_step only (ABI v13) */
 } GmpeStepOut;
 
 /* Teacher forcing for bit-parity runs.  NULL pointers = on-device Philox. */

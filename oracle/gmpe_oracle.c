@@ -1272,6 +1272,8 @@ static void step_world(World* w, const int32_t* act, const GmpeStepInject* inj, 
       double itmp[GMPE_INFO_K];
       double* info = out->info ? (double*)out->info + (w->b * N + i) * GMPE_INFO_K : itmp;
       july_info(w, i, info);
+      /* info['Phase_reached'] of the rot-inv family (tp:806, tp2:804, sc:840): phase_reached[agent.id] as reward(i) left it */
+      if (rot_inv(c) && out->phase_reached) out->phase_reached[w->b * N + i] = w->fl[i * 4 + GMPE_AF_PHASE_REACHED];
     }
   }
   double* r = (double*)out->reward + w->b * N;

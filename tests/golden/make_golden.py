@@ -207,6 +207,9 @@ def run_july_trace(path, seed, T, policy, eps=0.15, episodes=1, **over):
             rec["status"].append(status_after)
             rec["prev_phase"].append(np.array([ag.previous_phase for ag in w.agents]))
             rec["phase_reached"].append(sc.phase_reached.copy())
+            if "Phase_reached" in info_n[0]:  # rot-inv family (three_phase_graph.py:806): the info entry IS that array's value
+                assert [int(d["Phase_reached"]) for d in info_n] == [int(x) for x in sc.phase_reached], "info Phase_reached"
+                assert list(info_n[0]).index("Phase_reached") == list(info_n[0]).index("Min_time_to_goal") - 1
             rec["goal_reached"].append(sc.goal_reached.copy())
             rec["obs"].append(np.array(obs_n))
             rec["node_obs"].append(np.array(node_n))

@@ -31,7 +31,7 @@ class OracleEngine:
         self.out_arena = torch.zeros(max(off, 256), dtype=torch.uint8)
         self.out_slabs = offs
         self.out = {n: self.out_arena[o:o + nb].view(kinds[sh[n][1]]).view(sh[n][0]) for n, (o, nb) in offs.items()}
-        host_names = [n for n in names if n in ("obs", "node_obs", "adj", "reward", "done", "indiv_reward", "info")]
+        host_names = [n for n in names if n in ("obs", "node_obs", "adj", "reward", "done", "indiv_reward", "info", "phase_reached")]
         self.host_prefix_bytes = max(offs[n][0] + offs[n][1] for n in host_names)
         self.action_idx = torch.zeros((self.B, self.N), dtype=torch.int32)
         self.launch_count = 0

@@ -135,6 +135,10 @@ def test_fp64_free_running_with_auto_reset(case):
                 _cmp_real(g[k], o[k], tol, f"{case} t={t} {k}")
         for k in INT_OUT:
             assert (g[k].cpu().numpy() == o[k]).all(), f"{case} t={t} {k}"
+        if "phase_reached" in g:  # info['Phase_reached'] of the rot-inv family: terminal-step values survive the auto-reset
+            assert (g["phase_reached"].cpu().numpy() == o["phase_reached"]).all(), f"{case} t={t} phase_reached"
+        else:
+            assert not case.startswith(("three_phase", "two_phase", "corridor_rot_inv")), "rot-inv engines must emit phase_reached"
         for k in ("agent_state", "agent_aux", "world_f", "landmarks", "obstacles", "walls"):
             _cmp_real(eng.state[k], orc.state[k], 1e-9, f"{case} t={t} state.{k}")
         for k in ("agent_flags", "world_i", "agent_ext"):

@@ -65,6 +65,7 @@ def run_trace(tr: Trace, precision: str, teacher_force: bool, atol: float, rtol:
             assert (out["obs"][0][:, -1].cpu().numpy() == z["obs"][t][:, -1]).all(), tag + " phase"
             if tr.name.startswith(("three_phase", "two_phase", "corridor_rot_inv")):
                 assert (eng.state["agent_ext"][0, :, 0].cpu().numpy() == z["cooldown"][t]).all(), tag + " cooldown"
+                assert (out["phase_reached"][0].cpu().numpy() == z["phase_reached"][t]).all(), tag + " info Phase_reached"
                 if tr.name.startswith("corridor_rot_inv"):  # prev_proj: float32 bits in the second slot
                     pj = eng.state["agent_ext"][0, :, 1].cpu().numpy().view(np.float32)
                     assert np.abs(pj - z["prev_proj"][t]).max() <= max(atol, 1e-6), tag + " prev_proj"

@@ -142,6 +142,11 @@ def test_multi_agent_graph_env_replays_a_golden_episode_through_the_scenario_api
         np.testing.assert_allclose(np.array(rew_n), z["reward"][t], atol=tol)
         assert done_n == list(z["done"][t])
         assert info_n[1]["individual_reward"] == rew_n[1] and "Num_agent_collisions" in info_n[0]
+        if which.startswith("july"):
+            assert "Phase_reached" not in info_n[0]
+        else:  # the rot-inv family's extra info entry, in the reference's key order (three_phase_graph.py:788-811)
+            assert [d["Phase_reached"] for d in info_n] == [int(x) for x in z["phase_reached"][t]]
+            assert list(info_n[0])[-2:] == ["Phase_reached", "Min_time_to_goal"]
         # update_graph runs at the top of step() on the previous step's masked distances
         # (environment.py:1022-1023); the trace stores the list of step t under index t
         if t > 0:
@@ -210,6 +215,40 @@ def test_lazy_infos_are_fetched_on_access_and_guard_against_stale_reads():
             eager.step(act, 0)
     with pytest.raises(RuntimeError, match="earlier step"):
         first[0][0]["Dist_to_goal"]       # ... and stale by now
+    lazy.close(), eager.close()
+
+
+@pytest.mark.parametrize("output", ["numpy", "torch"])
+def test_rot_inv_infos_carry_phase_reached(output):
+    """info['Phase_reached'] (three_phase_graph.py:806) through the vec env: lazy and eager host paths and the
+    device-resident path agree with each other and with the state flags of worlds that did not auto-reset."""
+    from gmpe_b200 import default_args
+    from gmpe_b200.env_wrappers import GraphSubprocVecEnv
+
+    args = default_args(scenario_name="three_phase_graph", dynamics_type="air_taxi", world_size=3, episode_length=15,
+                        goal_rew=30, collaborative=False)
+    B = 257
+    kw = dict(args=args, num_envs=B, device=0, seed=9, output=output)
+    lazy, eager = GraphSubprocVecEnv(**kw), GraphSubprocVecEnv(lazy_info=False, **kw)
+    lazy.reset(), eager.reset()
+    rs = np.random.RandomState(3)
+    seen = set()
+    for t in range(32):
+        idx = rs.randint(25, size=(B, 3)).astype(np.int32)
+        act = torch.as_tensor(idx, device="cuda") if output == "torch" else np.eye(25)[idx]
+        ol, oe = lazy.step(act, 0), eager.step(act, 0)
+        if output == "torch":
+            pl, pe = ol[6]["phase_reached"].cpu().numpy(), oe[6]["phase_reached"].cpu().numpy()
+        else:
+            pl, pe = ol[6].phase_reached, oe[6].phase_reached
+            assert ol[6][B - 1][2]["Phase_reached"] == pe[B - 1, 2] and "Phase_reached" in oe[6][0][0].keys()
+        assert pl.dtype == np.uint8 and pl.shape == (B, 3) and np.array_equal(pl, pe)
+        fl = lazy.engine.state["agent_flags"].cpu().numpy()
+        step = lazy.engine.state["world_i"][:, abi.WI_STEP].cpu().numpy()
+        live = step > 0  # worlds that auto-reset this step show the terminal value in the info, 0 in the state
+        assert np.array_equal(pl[live], fl[live][:, :, abi.AF_PHASE_REACHED])
+        seen |= set(np.unique(pl).tolist())
+    assert 0 in seen and max(seen) <= 2, seen
     lazy.close(), eager.close()
 
 

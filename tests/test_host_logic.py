@@ -93,6 +93,13 @@ def test_lazy_infos_walks_like_process_infos():
             assert "individual_reward" in d.keys() and d["individual_reward"] == 7
             assert d["Dist_to_goal"] == info[e, a, 0] and d["Min_time_to_goal"] == info[e, a, 15]
             assert set(d.to_dict()) == {"individual_reward", *abi.INFO_KEYS}
+    # rot-inv family: 'Phase_reached' sits before 'Min_time_to_goal' (three_phase_graph.py:788-811)
+    ph = np.array([[0, 1, 2], [2, 1, 0]], dtype=np.uint8)
+    infos = LazyInfos(info, rew, phase_reached=ph)
+    d = infos[1][0]
+    assert list(d.keys())[-2:] == ["Phase_reached", "Min_time_to_goal"] and len(d) == 18
+    assert d["Phase_reached"] == 2 and infos[0][1]["Phase_reached"] == 1 and d["Min_time_to_goal"] == info[1, 0, 15]
+    assert "Phase_reached" not in LazyInfos(info, rew)[0][0]
 
 
 GLOO_WORKER = r'''

@@ -48,6 +48,8 @@ def run_trace(tr: Trace, use_rk45: bool, teacher_force_state: bool):
             assert (out["obs"][0][:, -1] == z["obs"][t][:, -1]).all(), (tr.name, t, "phase")
             if "agent_ext" in env.state and tr.name.startswith(("three_phase", "two_phase", "corridor_rot_inv")):
                 assert (env.state["agent_ext"][0, :, 0] == z["cooldown"][t]).all(), (tr.name, t, "cooldown")
+                # info['Phase_reached'] (three_phase_graph.py:806): the golden holds Scenario.phase_reached of the step
+                assert (out["phase_reached"][0] == z["phase_reached"][t]).all(), (tr.name, t, "info Phase_reached")
                 if tr.name.startswith("corridor_rot_inv"):  # prev_proj: float32 bits in the second slot
                     pp = np.ascontiguousarray(env.state["agent_ext"][0, :, 1]).view(np.float32)
                     assert np.abs(pp - z["prev_proj"][t]).max() <= 1e-6, (tr.name, t, "prev_proj")
