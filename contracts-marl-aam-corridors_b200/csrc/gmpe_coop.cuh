@@ -90,7 +90,10 @@ struct CoopTraits {
   static constexpr int EATTR_BYTES = up16(WPW * CAP * R) + 16;
   // 7-wide node rows (three_phase) are not whole sectors: the warp's rows are staged as one span
   static constexpr bool NODE_STAGED = ND != 8 || GMPE_COOP_STAGE_NODE;
-  static constexpr int NODE_BYTES = NODE_STAGED ? up16(AL * E * ND * R) + 16 : 0;
+  // widest rot-inv worlds (N = 14 .. 16): the node rows are staged and sent one WORLD at a time (a world's
+  // rows are one contiguous span too), which halves the region and lets a second CTA fit on the SM
+  static constexpr bool NODE_PER_WORLD = ND != 8 && N > 13 && WPW > 1;
+  static constexpr int NODE_BYTES = NODE_STAGED ? up16((NODE_PER_WORLD ? N : AL) * E * ND * R) + 16 : 0;
   static constexpr int ROUND_A = OBS_BYTES + ADJ_BYTES + NODE_BYTES;
   static constexpr int ROUND_B = EIDX_BYTES + EATTR_BYTES;
   // Bulk stores read the slab asynchronously: rounds A and B get separate regions when the
@@ -101,7 +104,7 @@ struct CoopTraits {
   // shared memory (wide rot-inv worlds, 11 <= N <= 16: up to 78 KB per warp in fp64)
   static constexpr int SLAB_MIN = up16(ROUND_A > ROUND_B ? ROUND_A : ROUND_B);
   static constexpr int WARPS = SLAB_MIN * GMPE_COOP_WARPS <= 220 * 1024 ? GMPE_COOP_WARPS : (SLAB_MIN * 2 <= 220 * 1024 ? 2 : 1);
-  static constexpr int MINBLOCKS = N > 10 ? 1 : N > 5 ? (R == 4 ? GMPE_COOP_MINBLOCKS_N6 : 1) : (N > 3 ? (R == 4 ? GMPE_COOP_MINBLOCKS_N4 : 2) : (R == 4 ? (ROT_INV ? GMPE_COOP_MINBLOCKS_TP : (SCEN == GMPE_SCEN_NAV_GRAPH ? GMPE_COOP_MINBLOCKS_NAV : GMPE_COOP_MINBLOCKS_F32)) : GMPE_COOP_MINBLOCKS_F64));
+  static constexpr int MINBLOCKS = N > 10 ? 2 : N > 5 ? (R == 4 ? GMPE_COOP_MINBLOCKS_N6 : 1) : (N > 3 ? (R == 4 ? GMPE_COOP_MINBLOCKS_N4 : 2) : (R == 4 ? (ROT_INV ? GMPE_COOP_MINBLOCKS_TP : (SCEN == GMPE_SCEN_NAV_GRAPH ? GMPE_COOP_MINBLOCKS_NAV : GMPE_COOP_MINBLOCKS_F32)) : GMPE_COOP_MINBLOCKS_F64));
   static constexpr bool SPLIT = GMPE_COOP_BULK_STORE && (up16(ROUND_A + ROUND_B) + 0) * WARPS * MINBLOCKS <= 220 * 1024;
   static constexpr int B_OFF = SPLIT ? ROUND_A : 0;
   static constexpr int SLAB_BYTES = SPLIT ? up16(ROUND_A + ROUND_B) : up16(ROUND_A > ROUND_B ? ROUND_A : ROUND_B);
@@ -840,10 +843,13 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         for (int q = 0; q < E; ++q) { adj_s[i * E + q] = row_a[q]; adj_s[(N + i) * E + q] = row_l[q]; }
       }
     }
-    if (ND != 8 && lane_used && g_nodew) {
+    // node rows of world `nw_` of the warp (NODE_PER_WORLD) or of every world at once (nw_ < 0)
+    auto stage_node_rows = [&](int nw_) {
+    if (ND != 8 && lane_used && g_nodew && (nw_ < 0 || wl == nw_)) {
       // _get_entity_feat_relative (tp:1391-1430): float32 differences rotated into the ego's
       // (post-reward) heading frame; [rel_vel, rel_pos, rel_goal, type], 7 Reals per node
-      Real* nd = reinterpret_cast<Real*>(node_region + (reinterpret_cast<size_t>(g_nodew) & 15)) + lane * (E * ND);
+      const Real* gspan = nw_ < 0 ? g_nodew : g_nodew + (size_t)nw_ * (N * E * ND);
+      Real* nd = reinterpret_cast<Real*>(node_region + (reinterpret_cast<size_t>(gspan) & 15)) + (nw_ < 0 ? lane : i) * (E * ND);
       const Real pex = trunc32(s.x), pey = trunc32(s.y), vex = trunc32(vpost.x), vey = trunc32(vpost.y);
 #pragma unroll
       for (int k = 0; k < E; ++k) {
@@ -867,6 +873,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
         nd[k * ND + 6] = f[6];
       }
     }
+    };
+    stage_node_rows(T::NODE_PER_WORLD ? 0 : -1);
     if (adj_direct && wr && p.out.adj) {  // two rows of E Reals each, 8/16-byte aligned (E is even)
       V2* ra = reinterpret_cast<V2*>((Real*)p.out.adj + (size_t)b * EE + (size_t)i * E);
       V2* rl = reinterpret_cast<V2*>((Real*)p.out.adj + (size_t)b * EE + (size_t)(N + i) * E);
@@ -878,9 +886,25 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       __syncwarp();
       if (!obs_direct && g_obs) copy_span<Real, N * F>(g_obs, obs_region, nwv * N * F, all_worlds, wmask, lane);
       if (!adj_direct && g_adj) copy_span<Real, EE>(g_adj, adj_region, nwv * EE, all_worlds, wmask, lane);
-      if (T::NODE_STAGED && g_nodew) copy_span<Real, N * E * ND>(g_nodew, node_region, nwv * N * E * ND, all_worlds, wmask, lane);
+      if (T::NODE_STAGED && g_nodew) {
+        if (!T::NODE_PER_WORLD) copy_span<Real, N * E * ND>(g_nodew, node_region, nwv * N * E * ND, all_worlds, wmask, lane);
+        else if (wmask & 1u) copy_span<Real, N * E * ND>(g_nodew, node_region, N * E * ND, true, 1u, lane);
+      }
       if (GMPE_COOP_BULK_STORE && lane == 0) bulk_commit();
       __syncwarp();
+      if (T::NODE_PER_WORLD && g_nodew) {
+#pragma unroll 1
+        for (int w = 1; w < WPW; ++w) {
+          if (w >= nwv) break;  // uniform
+          drain();  // the previous world's rows have left the region
+          stage_node_rows(w);
+          if (GMPE_COOP_BULK_STORE) fence_async_smem();
+          __syncwarp();
+          if ((wmask >> w) & 1u) copy_span<Real, N * E * ND>(g_nodew + (size_t)w * (N * E * ND), node_region, N * E * ND, true, 1u, lane);
+          if (GMPE_COOP_BULK_STORE && lane == 0) bulk_commit();
+          __syncwarp();
+        }
+      }
     }
 
     // ---------------- emission: edge lists (staged, round B, once per list) ---------------------
