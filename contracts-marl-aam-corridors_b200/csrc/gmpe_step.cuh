@@ -565,6 +565,13 @@ constexpr int kEdgeUnroll = GMPE_EDGE_UNROLL;
 #define GMPE_EDGE_UNROLL_MID 8
 #endif
 constexpr int kEdgeUnrollMid = GMPE_EDGE_UNROLL_MID;
+#ifndef GMPE_EDGE_LINEAR  // 1: linear walk of the E*E matrix for compile-time E that is not a multiple of 32 (see the edge emission)
+#define GMPE_EDGE_LINEAR 1
+#endif
+#ifndef GMPE_EDGE_LINEAR_UNROLL
+#define GMPE_EDGE_LINEAR_UNROLL 8
+#endif
+constexpr int kEdgeLinearUnroll = GMPE_EDGE_LINEAR_UNROLL;
 #ifndef GMPE_FORCE_UNROLL  // pair loop of the force physics: independent MUFU chains overlap (N = 16: 226.3 -> 223.2 us with 8)
 #define GMPE_FORCE_UNROLL 8
 #endif
@@ -1192,6 +1199,54 @@ __global__ void __launch_bounds__(GMPE_LB_THREADS, GMPE_LB_MINBLOCKS) gmpe_step_
           int32_t* gi = gnn_e ? p.out.gnn_edge_index + gb * 2 * cap : nullptr;
           Real* gea = gnn_e ? (Real*)p.out.gnn_edge_attr + gb * cap : nullptr;
           Real* g_adjw = p.out.adj ? (Real*)p.out.adj + gb * EE : nullptr;  // masked distance matrix, one copy per world (july:1625-1648)
+          if constexpr (EC > 0 && (EC % 32) != 0 && GMPE_EDGE_LINEAR) {
+            // Compile-time entity count that is not a multiple of the warp (E = 44): walk the E*E matrix
+            // LINEARLY in chunks of 32 entries instead of row by row.  Row-major order is kept (the ballot
+            // order inside a chunk is the matrix order), every lane is busy in every chunk but the last
+            // (61 chunks against 44 x 2 half-empty row groups), and each adjacency store is one whole,
+            // aligned 128-byte line (a world's matrix starts on a 32-byte boundary) instead of a 176-byte
+            // row cut into a 128- and a 48-byte piece at odd 16-byte offsets.
+            constexpr int EEC = EC * EC;
+            int n_env = 0, n_gnn = 0;
+#pragma unroll kEdgeLinearUnroll
+            for (int q0 = 0; q0 < EEC; q0 += 32) {
+              const int q = q0 + lane;
+              const bool in = q < EEC;
+              const int r = in ? q / EC : 0, cg = in ? q - r * EC : 0;
+              const V2 a = pw[r], bq = pw[cg];
+              const bool offd = !in || r == cg || mk[r] != 0 || mk[cg] != 0;
+              const Real d = offd ? Real(0) : norm2(a.x - bq.x, a.y - bq.y);
+              if (g_adjw && in) g_adjw[q] = d;
+              if (env_e) {  // update_graph: (d <= max_edge_dist) & (d > 0), row-major (july:1660-1665)
+                const bool on = d > Real(0) && d <= thr_env;
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) {
+                  const int slot = n_env + __popc(m & lt);
+                  ei[slot] = r; ei[cap + slot] = cg; ea[slot] = d;
+                }
+                n_env += __popc(m);
+              }
+              if (gnn_e) {  // process_adj on the fp32 cast: (adj < max_edge_dist) & (adj > 0) (gnn_new.py:339)
+                const float df = (float)d;
+                const bool on = df > 0.0f && df < thr_gnn;
+                const unsigned m = __ballot_sync(0xffffffffu, on);
+                if (on) {
+                  const int slot = n_gnn + __popc(m & lt);
+                  gi[slot] = r; gi[cap + slot] = cg; gea[slot] = Real(df);
+                }
+                n_gnn += __popc(m);
+              }
+            }
+            if (env_e) {
+              for (int q = n_env + lane; q < cap; q += 32) { ei[q] = -1; ei[cap + q] = -1; ea[q] = Real(0); }
+              if (lane == 0) p.out.num_edges[gb] = n_env;
+            }
+            if (gnn_e) {
+              for (int q = n_gnn + lane; q < cap; q += 32) { gi[q] = -1; gi[cap + q] = -1; gea[q] = Real(0); }
+              if (lane == 0) p.out.gnn_num_edges[gb] = n_gnn;
+            }
+            continue;
+          }
           V2 bcol[MAXG];
           uint32_t offm = 0, has = 0;  // bit g: the lane's column of group g is masked / exists
 #pragma unroll
