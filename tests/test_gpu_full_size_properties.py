@@ -107,7 +107,7 @@ WIDE = dict(scenario_name="nav_graph_metered_single_corridor_rot_inv", dynamics_
 
 @pytest.mark.parametrize("precision", ["fp32", "fp64"])
 def test_wide_rot_inv_worlds_do_not_depend_on_the_sharding(precision):
-    """The wide lane-per-agent instantiations (N = 16: two worlds per warp, 4 warps per CTA in fp32, 2 in fp64):
+    """The wide lane-per-agent instantiations (N = 16: two worlds per warp, node rows staged one world at a time):
     an odd batch (partial last group, transposed tail) and a shard of it agree bit for bit through auto-resets."""
     B, B0, Bs, T = 2051, 1025, 513, 14
     cfg, big = _run(WIDE, B, T, precision=precision)
