@@ -580,7 +580,7 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   memset(&p, 0, sizeof(p));
   p.c = c;
   p.st = *st;
-  p.out = *out;
+  GmpeStepOut o = *out;
   p.act = act;
   p.env_mask = mask;
   p.theta = inj ? inj->theta_draw : nullptr;
@@ -598,7 +598,7 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
   if (b0 != 0 || count != c.num_worlds) {  // a slice of the batch: same arrays, re-based on world b0
     const int64_t R = c.precision == GMPE_F64 ? 8 : 4;
     rebase_state(p.st, c, b0, R);
-    rebase_out(p.out, c, b0, R);
+    rebase_out(o, c, b0, R);
     if (p.has_rst) rebase_state(p.rst, c, b0, R);
     shift(p.act, b0 * c.num_agents);
     shift(p.env_mask, b0);
@@ -609,6 +609,8 @@ static int launch(gmpe_handle h, int mode, const GmpeState* st, const int32_t* a
     p.num_tiles = (int)((count + h->wpb - 1) / h->wpb);
     grid = grid_for(h, p.num_tiles);
   }
+  memcpy(&p.out, &o, sizeof(p.out));  // the leading fifteen pointers (KOut) ...
+  p.out_phase_reached = o.phase_reached;  // ... and the sixteenth, kept at the end of the parameter block
   p.stage_graph = h->stage_graph;
   memcpy(p.act_tab_c, h->act_tab_host, sizeof(p.act_tab_c));
   if (h->small == KERNEL_COOP) {  // round structure of the persistent grid (num_tiles counts CTAs of coop_warps warps)

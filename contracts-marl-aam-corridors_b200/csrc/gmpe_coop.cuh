@@ -572,7 +572,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
           store_row8(gi, lo);
           store_row8(gi + 8, hi);
         }
-        if (tp && valid && p.out.phase_reached) p.out.phase_reached[ga] = (uint8_t)pr;  // info['Phase_reached'] (tp:806, tp2:804, sc:840)
+        if (tp && valid && p.out_phase_reached) p.out_phase_reached[ga] = (uint8_t)pr;  // info['Phase_reached'] (tp:806, tp2:804, sc:840)
       }
       if (valid) {
         const bool collab = (c.flags & GMPE_FLAG_COLLABORATIVE) != 0;

@@ -28,10 +28,31 @@ namespace gmpe {
 
 enum { MODE_STEP = 0, MODE_RESET = 1 };
 
+// The first fifteen pointers of GmpeStepOut (everything but phase_reached, which the parameter block carries at
+// its END as out_phase_reached).  The tile kernels proved sensitive to the offsets of the parameter block: with the
+// sixteenth pointer in place here -- every later field 8 bytes further on -- the same source compiled to a
+// different schedule and the N = 64 / N = 16 instantiations ran 6 % / 4 % slower (same-box A/B,
+// profiles/r2_sweep.txt), so the fields those kernels read keep the offsets they had.
+struct KOut {
+  void *obs, *node_obs, *adj, *reward;
+  uint8_t* done;
+  void* info;
+  int32_t* edge_index;
+  void* edge_attr;
+  int32_t *num_edges, *gnn_edge_index;
+  void* gnn_edge_attr;
+  int32_t* gnn_num_edges;
+  void* indiv_reward;
+  float *mask, *active_mask;
+};
+static_assert(sizeof(KOut) == 15 * sizeof(void*) && offsetof(GmpeStepOut, phase_reached) == sizeof(KOut) &&
+              offsetof(KOut, active_mask) == offsetof(GmpeStepOut, active_mask) && offsetof(KOut, info) == offsetof(GmpeStepOut, info),
+              "KOut mirrors the leading fields of GmpeStepOut");
+
 struct KParams {
   GmpeConfig c;
   GmpeState st;
-  GmpeStepOut out;
+  KOut out;
   GmpeState rst;  // injected reset state (valid when has_rst)
   const int32_t* act;
   const void* theta;
@@ -55,6 +76,7 @@ struct KParams {
   int coop_groups;       // ceil(worlds of the launch / worlds per warp)
   int coop_full_rounds;  // coop_groups / (grid * warps per CTA)
   alignas(16) unsigned char act_tab_c[512];
+  uint8_t* out_phase_reached;  // GmpeStepOut.phase_reached (rot-inv family, lane-per-agent kernel only)
 };
 
 // ---- shared memory carve-up --------------------------------------------------------
