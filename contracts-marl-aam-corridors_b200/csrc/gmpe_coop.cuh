@@ -93,7 +93,12 @@ struct CoopTraits {
   // widest rot-inv worlds (N = 14 .. 16): the node rows are staged and sent one WORLD at a time (a world's
   // rows are one contiguous span too), which halves the region and lets a second CTA fit on the SM
   static constexpr bool NODE_PER_WORLD = ND != 8 && N > 13 && WPW > 1;
-  static constexpr int NODE_BYTES = NODE_STAGED ? up16((NODE_PER_WORLD ? N : AL) * E * ND * R) + 16 : 0;
+  // N = 16: a lane's block of staged node rows is E * ND = 224 Reals, a multiple of 32 words, so every lane of the
+  // warp would write the same shared-memory bank.  The blocks are then kept 16 bytes apart and each leaves through
+  // its own bulk copy (896 / 1792 bytes, 16-byte aligned on both sides at that shape) instead of one span per world.
+  static constexpr int NODE_LANE = E * ND;
+  static constexpr int NODE_PAD = (NODE_PER_WORLD && (NODE_LANE * R / 4) % 32 == 0 && (NODE_LANE * R) % 16 == 0) ? 16 / R : 0;
+  static constexpr int NODE_BYTES = NODE_STAGED ? up16((NODE_PER_WORLD ? N : AL) * (NODE_LANE + NODE_PAD) * R) + 16 : 0;
   static constexpr int ROUND_A = OBS_BYTES + ADJ_BYTES + NODE_BYTES;
   static constexpr int ROUND_B = EIDX_BYTES + EATTR_BYTES;
   // Bulk stores read the slab asynchronously: rounds A and B get separate regions when the
@@ -184,7 +189,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
   unsigned char* slab = smem_raw + (size_t)warp * T::SLAB_BYTES;
   auto drain = [&]() {
     if (GMPE_COOP_BULK_STORE) {
-      if (lane == 0) bulk_wait_read();
+      if (lane == 0 || T::NODE_PAD) bulk_wait_read();  // padded node blocks: every lane waits for the copies it issued itself
       __syncwarp();
     }
   };
@@ -748,7 +753,9 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     // obs rows whose byte length is a multiple of 8 (navigation: 6 Reals) leave the lane as
     // 64/128-bit stores; the 19-wide july rows are staged and streamed out as one span
     constexpr bool obs_direct = GMPE_COOP_DIRECT_SMALL_ROWS && (F % 2) == 0;
-    constexpr bool adj_direct = GMPE_COOP_DIRECT_SMALL_ROWS != 0;
+    // E = 32 (N = 16): staged adjacency rows would start 32 words apart -- every lane of the warp on one bank --
+    // so the two rows of a lane (128 bytes each) go straight to global memory instead
+    constexpr bool adj_direct = GMPE_COOP_DIRECT_SMALL_ROWS != 0 || (E % 32) == 0;
     Real* g_adj = p.out.adj ? (Real*)p.out.adj + (size_t)wbase * EE : nullptr;
     unsigned char* obs_region = slab;
     unsigned char* adj_region = slab + T::OBS_BYTES;
@@ -849,7 +856,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       // _get_entity_feat_relative (tp:1391-1430): float32 differences rotated into the ego's
       // (post-reward) heading frame; [rel_vel, rel_pos, rel_goal, type], 7 Reals per node
       const Real* gspan = nw_ < 0 ? g_nodew : g_nodew + (size_t)nw_ * (N * E * ND);
-      Real* nd = reinterpret_cast<Real*>(node_region + (reinterpret_cast<size_t>(gspan) & 15)) + (nw_ < 0 ? lane : i) * (E * ND);
+      Real* nd = T::NODE_PAD ? reinterpret_cast<Real*>(node_region) + i * (T::NODE_LANE + T::NODE_PAD)
+                             : reinterpret_cast<Real*>(node_region + (reinterpret_cast<size_t>(gspan) & 15)) + (nw_ < 0 ? lane : i) * (E * ND);
       const Real pex = trunc32(s.x), pey = trunc32(s.y), vex = trunc32(vpost.x), vey = trunc32(vpost.y);
 #pragma unroll
       for (int k = 0; k < E; ++k) {
@@ -875,6 +883,20 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
     }
     };
     stage_node_rows(T::NODE_PER_WORLD ? 0 : -1);
+    // one world's padded node blocks -> global: a bulk copy per lane block, or plain stores for a misaligned caller buffer
+    auto send_node_world = [&](Real* gw) {
+      if (T::NODE_PAD) {
+        const Real* src = reinterpret_cast<const Real*>(node_region);
+        if (GMPE_COOP_BULK_STORE && (reinterpret_cast<size_t>(gw) & 15) == 0) {
+          if (lane < N) bulk_store_issue(gw + lane * T::NODE_LANE, src + lane * (T::NODE_LANE + T::NODE_PAD), (uint32_t)(T::NODE_LANE * T::R));
+        } else {
+#pragma unroll 1
+          for (int q = lane; q < N * T::NODE_LANE; q += 32) gw[q] = src[q + (q / T::NODE_LANE) * T::NODE_PAD];
+        }
+      } else {
+        copy_span<Real, N * E * ND>(gw, node_region, N * E * ND, true, 1u, lane);
+      }
+    };
     if (adj_direct && wr && p.out.adj) {  // two rows of E Reals each, 8/16-byte aligned (E is even)
       V2* ra = reinterpret_cast<V2*>((Real*)p.out.adj + (size_t)b * EE + (size_t)i * E);
       V2* rl = reinterpret_cast<V2*>((Real*)p.out.adj + (size_t)b * EE + (size_t)(N + i) * E);
@@ -888,9 +910,9 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       if (!adj_direct && g_adj) copy_span<Real, EE>(g_adj, adj_region, nwv * EE, all_worlds, wmask, lane);
       if (T::NODE_STAGED && g_nodew) {
         if (!T::NODE_PER_WORLD) copy_span<Real, N * E * ND>(g_nodew, node_region, nwv * N * E * ND, all_worlds, wmask, lane);
-        else if (wmask & 1u) copy_span<Real, N * E * ND>(g_nodew, node_region, N * E * ND, true, 1u, lane);
+        else if (wmask & 1u) send_node_world(g_nodew);
       }
-      if (GMPE_COOP_BULK_STORE && lane == 0) bulk_commit();
+      if (GMPE_COOP_BULK_STORE && (lane == 0 || (T::NODE_PAD && lane < N))) bulk_commit();
       __syncwarp();
       if (T::NODE_PER_WORLD && g_nodew) {
 #pragma unroll 1
@@ -900,8 +922,8 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
           stage_node_rows(w);
           if (GMPE_COOP_BULK_STORE) fence_async_smem();
           __syncwarp();
-          if ((wmask >> w) & 1u) copy_span<Real, N * E * ND>(g_nodew + (size_t)w * (N * E * ND), node_region, N * E * ND, true, 1u, lane);
-          if (GMPE_COOP_BULK_STORE && lane == 0) bulk_commit();
+          if ((wmask >> w) & 1u) send_node_world(g_nodew + (size_t)w * (N * E * ND));
+          if (GMPE_COOP_BULK_STORE && (lane == 0 || (T::NODE_PAD && lane < N))) bulk_commit();
           __syncwarp();
         }
       }
@@ -989,7 +1011,7 @@ gmpe_step_coop_kernel(const __grid_constant__ KParams p) {
       __syncwarp();
     }
   }
-  if (GMPE_COOP_BULK_STORE && lane == 0) bulk_wait_read();  // shared memory stays allocated until the copies have read it
+  if (GMPE_COOP_BULK_STORE && (lane == 0 || CoopTraits<Real, SCEN, N>::NODE_PAD)) bulk_wait_read();  // shared memory stays allocated until the copies have read it
 }
 
 }  // namespace gmpe
